@@ -1,0 +1,117 @@
+"""ctypes binding of include/sctda_b200.h.
+
+There is no CPU fallback: if the shared library is missing, or no B200 is visible when a
+context is created, the calls raise.  Torch is used only as the owner of device memory and
+streams; no torch type crosses the C-ABI (plain pointers and sizes).
+"""
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, 'csrc', 'libsctda_b200.so')
+
+c_i32 = ctypes.c_int32
+c_i64 = ctypes.c_int64
+c_f64 = ctypes.c_double
+c_ptr = ctypes.c_void_p
+
+SCTDA_OK = 0
+ERR_NAMES = {-1: 'SCTDA_ERR_INVALID', -2: 'SCTDA_ERR_CUDA', -3: 'SCTDA_ERR_NOMEM', -4: 'SCTDA_ERR_UNSUPPORTED'}
+
+
+class SctdaError(RuntimeError):
+    def __init__(self, code, msg):
+        RuntimeError.__init__(self, '%s (%d): %s' % (ERR_NAMES.get(code, 'error'), code, msg))
+        self.code = code
+
+
+class Graph(ctypes.Structure):
+    """struct sctda_graph."""
+    _fields_ = [('V', c_i32), ('S', c_i32), ('Ncells', c_i32), ('reserved', c_i32),
+                ('d_node_off', c_ptr), ('d_node_cols', c_ptr), ('d_adj_off', c_ptr),
+                ('d_adj_idx', c_ptr), ('d_adj_w', c_ptr), ('d_samples', c_ptr)]
+
+
+# name -> (restype, argtypes); every symbol include/sctda_b200.h declares
+SIGNATURES = {
+    'sctda_abi_version': (c_i32, []),
+    'sctda_ctx_create': (c_i32, [c_i32, ctypes.POINTER(c_ptr)]),
+    'sctda_ctx_destroy': (c_i32, [c_ptr]),
+    'sctda_last_error': (ctypes.c_char_p, [c_ptr]),
+    'sctda_workspace_bytes': (c_i64, [c_ptr]),
+    'sctda_launch_count': (c_i64, [c_ptr]),
+    'sctda_node_stats': (c_i32, [c_ptr, ctypes.POINTER(Graph), c_i32, c_ptr, c_i64, c_i32, c_ptr,
+                                 c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
+    'sctda_conn_perm_test': (c_i32, [c_ptr, ctypes.POINTER(Graph), c_i32, c_ptr, c_i64, c_i32,
+                                     c_i32, c_ptr, c_i64, c_ptr, c_f64, c_ptr, c_ptr, c_ptr, c_ptr]),
+}
+
+_lib = None
+
+
+def load():
+    """Loads libsctda_b200.so (built by sctda_b200.build / __graft_entry__.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError('%s is missing: run `python -m sctda_b200.build` (there is no CPU fallback)' % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the header and the library disagree
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (None -> NULL)."""
+    if t is None:
+        return None
+    return ctypes.c_void_p(t.data_ptr())
+
+
+class Context(object):
+    """One sctda_ctx on one GPU."""
+
+    def __init__(self, device=0):
+        self.lib = load()
+        h = c_ptr()
+        rc = self.lib.sctda_ctx_create(int(device), ctypes.byref(h))
+        if rc != SCTDA_OK:
+            raise SctdaError(rc, 'sctda_ctx_create(device=%d) failed: a B200 (sm_100a) GPU is required; '
+                                 'there is no CPU fallback' % device)
+        self.handle = h
+        self.device = int(device)
+
+    def check(self, rc):
+        if rc != SCTDA_OK:
+            raise SctdaError(rc, self.lib.sctda_last_error(self.handle).decode())
+
+    def launch_count(self):
+        return int(self.lib.sctda_launch_count(self.handle))
+
+    def workspace_bytes(self):
+        return int(self.lib.sctda_workspace_bytes(self.handle))
+
+    def close(self):
+        if self.handle is not None:
+            self.lib.sctda_ctx_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_contexts = {}
+
+
+def context(device=0):
+    """Process-wide context per device."""
+    if device not in _contexts:
+        _contexts[device] = Context(device)
+    return _contexts[device]

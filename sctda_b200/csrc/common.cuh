@@ -1,0 +1,87 @@
+// Shared internals of libsctda_b200.so: the context, the workspace and the error convention
+// of include/sctda_b200.h.  Nothing here is visible through the C-ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/sctda_b200.h"
+
+#define SCTDA_NUM_SLOTS 16
+
+struct sctda_ctx {
+    int device;
+    int sm_count;
+    char err[512];
+    void* slot_ptr[SCTDA_NUM_SLOTS];     // grow-only device workspace, one buffer per slot
+    size_t slot_bytes[SCTDA_NUM_SLOTS];
+    int64_t launches;
+};
+
+// Workspace slots (one live use per call; calls on one context are serialised by contract).
+enum {
+    WS_ET = 0,        // transformed, transposed expression tiles
+    WS_PM = 1,        // per-CTA node value scratch
+    WS_MISC = 2,
+    WS_DIST_XN = 3,   // normalised rows for the distance kernel
+    WS_COVER = 4,
+    WS_CLUSTER = 5,
+    WS_NERVE = 6,
+    WS_CLUSTER2 = 7,
+    WS_CLUSTER3 = 8,
+};
+
+static inline int sctda_fail(sctda_ctx* ctx, int code, const char* fmt, const char* a = "", long long b = 0) {
+    if (ctx) snprintf(ctx->err, sizeof(ctx->err), fmt, a, b);
+    return code;
+}
+
+#define SCTDA_CUDA(ctx, call)                                                              \
+    do {                                                                                   \
+        cudaError_t e_ = (call);                                                           \
+        if (e_ != cudaSuccess) {                                                           \
+            snprintf((ctx)->err, sizeof((ctx)->err), "%s failed at %s:%d: %s", #call,      \
+                     __FILE__, __LINE__, cudaGetErrorString(e_));                          \
+            return SCTDA_ERR_CUDA;                                                         \
+        }                                                                                  \
+    } while (0)
+
+#define SCTDA_LAUNCH_CHECK(ctx, name)                                                      \
+    do {                                                                                   \
+        (ctx)->launches++;                                                                 \
+        cudaError_t e_ = cudaGetLastError();                                               \
+        if (e_ != cudaSuccess) {                                                           \
+            snprintf((ctx)->err, sizeof((ctx)->err), "launch of %s failed: %s", name,      \
+                     cudaGetErrorString(e_));                                              \
+            return SCTDA_ERR_CUDA;                                                         \
+        }                                                                                  \
+    } while (0)
+
+// Returns a device buffer of at least `bytes` in `slot` (contents undefined), or NULL.
+static inline void* sctda_ws(sctda_ctx* ctx, int slot, size_t bytes) {
+    if (bytes == 0) bytes = 256;
+    if (ctx->slot_bytes[slot] >= bytes) return ctx->slot_ptr[slot];
+    if (ctx->slot_ptr[slot]) {
+        cudaDeviceSynchronize();          // earlier stream work may still read the old buffer
+        cudaFree(ctx->slot_ptr[slot]);
+        ctx->slot_ptr[slot] = nullptr;
+        ctx->slot_bytes[slot] = 0;
+    }
+    size_t want = bytes + bytes / 8;      // slack so that slowly growing requests do not thrash
+    void* p = nullptr;
+    if (cudaMalloc(&p, want) != cudaSuccess) {
+        cudaGetLastError();
+        want = bytes;
+        if (cudaMalloc(&p, want) != cudaSuccess) {
+            cudaGetLastError();
+            snprintf(ctx->err, sizeof(ctx->err), "workspace slot %d: cudaMalloc of %zu bytes failed", slot, bytes);
+            return nullptr;
+        }
+    }
+    ctx->slot_ptr[slot] = p;
+    ctx->slot_bytes[slot] = want;
+    return p;
+}
+
+static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }

@@ -1,0 +1,461 @@
+"""Host-side mirror of scTDA.UnrootedGraph / scTDA.RootedGraph for the hot path (b):
+same constructor arguments, method names, return values and file formats as the reference
+(/root/reference/scTDA/main.py, "ref:"), with the per-gene work done in batches by the CUDA
+kernels behind include/sctda_b200.h.  No CPU fallback: every statistic comes from the GPU.
+
+Mirrored: __init__ (ref:785-891), get_gene (ref:893-964), connectivity_pvalue (ref:966-992),
+connectivity (ref:994-1005), delta (ref:1007-1028), expr (ref:1030-1051), save (ref:1053-1086),
+benjamini_hochberg (ref:92-115); RootedGraph.__init__ root/pseudo-time state (ref:1522-1567),
+centroid (ref:1724-1743), save (ref:1879-1914).
+Not mirrored (SURVEY.md §2 "out of scope"): layouts, pickles, drawing, plotting.
+"""
+import json
+
+import networkx
+import numpy
+import scipy.sparse
+import scipy.sparse.csgraph
+import scipy.stats
+import torch
+
+from . import _lib
+from . import formats
+
+
+def benjamini_hochberg(pvalues):
+    """BH step-up q-values with the reference's tie order (ref:92-115): p sorted descending,
+    equal p by descending index; q = running minimum of (n/rank) * p."""
+    p = numpy.asarray(pvalues, dtype=numpy.float64)
+    n = p.shape[0]
+    if n == 0:
+        return []
+    order = numpy.lexsort((numpy.arange(n), p))[::-1]
+    rank = float(n) - numpy.arange(n, dtype=numpy.float64)
+    vals = (float(n) / rank) * p[order]
+    vals = numpy.minimum.accumulate(vals)
+    out = numpy.empty(n, dtype=numpy.float64)
+    out[order] = vals
+    return list(out)
+
+
+def reference_perm_indices(n, S, rng=None):
+    """The permutation source of ref:975-976 as index arrays: row r of an n x S block is
+    arange(S) shuffled by numpy.random.shuffle, rows in order, from the GLOBAL legacy
+    MT19937 stream (or `rng`).  Fisher-Yates never looks at the values, so the draws are
+    those the reference consumes and shuffled_row == row[perm[r]]."""
+    rng = numpy.random if rng is None else rng
+    out = numpy.empty((n, S), dtype=numpy.int32)
+    base = numpy.arange(S, dtype=numpy.int32)
+    for r in range(n):
+        out[r] = base
+        rng.shuffle(out[r])
+    return out
+
+
+class DeviceGraph(object):
+    """Device image of (pl, adj, dic, samples): struct sctda_graph (include/sctda_b200.h)."""
+
+    def __init__(self, node_members, adj_csr, samples, n_cells, device):
+        """node_members: list of int sequences (table rows), in node order;
+        adj_csr: scipy CSR V x V float64 in the same node order; samples: int array."""
+        dev = torch.device('cuda', device)
+        samples = numpy.asarray(samples, dtype=numpy.int64)
+        V = len(node_members)
+        pos = numpy.full(int(samples.max()) + 1 if samples.size else 1, -1, dtype=numpy.int64)
+        pos[samples] = numpy.arange(samples.size)                     # koi of ref:973-974
+        sizes = numpy.array([len(m) for m in node_members], dtype=numpy.int64)
+        off = numpy.zeros(V + 1, dtype=numpy.int64)
+        numpy.cumsum(sizes, out=off[1:])
+        flat = numpy.concatenate([numpy.asarray(m, dtype=numpy.int64) for m in node_members]) if V else numpy.zeros(0, numpy.int64)
+        cols = pos[flat]
+        if (cols < 0).any() or (sizes == 0).any():
+            raise ValueError('node member lists must be non-empty and contained in samples')
+        if off[-1] >= 2 ** 31 or samples.size >= 2 ** 31:
+            raise ValueError('graph too large for int32 indices')
+        adj_csr = scipy.sparse.csr_matrix(adj_csr, dtype=numpy.float64)
+        self.V, self.S, self.Ncells = V, int(samples.size), int(n_cells)
+        self.Mtot = int(off[-1])
+        self.nnz = int(adj_csr.nnz)
+        self.node_off = torch.from_numpy(off.astype(numpy.int32)).to(dev)
+        self.node_cols = torch.from_numpy(cols.astype(numpy.int32)).to(dev)
+        self.adj_off = torch.from_numpy(adj_csr.indptr.astype(numpy.int32)).to(dev)
+        self.adj_idx = torch.from_numpy(adj_csr.indices.astype(numpy.int32)).to(dev)
+        self.adj_w = torch.from_numpy(adj_csr.data.astype(numpy.float64)).to(dev)
+        self.samples = torch.from_numpy(samples.astype(numpy.int32)).to(dev)
+        self.device = dev
+        self.struct = _lib.Graph(V=self.V, S=self.S, Ncells=self.Ncells, reserved=0,
+                                 d_node_off=self.node_off.data_ptr(), d_node_cols=self.node_cols.data_ptr(),
+                                 d_adj_off=self.adj_off.data_ptr(), d_adj_idx=self.adj_idx.data_ptr(),
+                                 d_adj_w=self.adj_w.data_ptr(), d_samples=self.samples.data_ptr())
+
+
+def node_stats(ctx, dg, Y, log2=True, dist=None, want_p=False):
+    """sctda_node_stats on a device table Y [G, >=Ncells] (float64, gene-major).
+    Returns a dict of device tensors."""
+    import ctypes
+    G = int(Y.shape[0])
+    dev = dg.device
+    out = {'expr': torch.empty(G, dtype=torch.int32, device=dev)}
+    for k in ('tol', 'mean', 'min', 'max', 'conn'):
+        out[k] = torch.empty(G, dtype=torch.float64, device=dev)
+    if dist is not None:
+        out['cen'] = torch.empty(G, dtype=torch.float64, device=dev)
+        out['disp'] = torch.empty(G, dtype=torch.float64, device=dev)
+    if want_p:
+        out['p'] = torch.empty((G, dg.V), dtype=torch.float64, device=dev)
+    p = _lib.ptr
+    rc = ctx.lib.sctda_node_stats(ctx.handle, ctypes.byref(dg.struct), G, p(Y), int(Y.stride(0)) if G else dg.Ncells,
+                                  1 if log2 else 0, p(dist), p(out['expr']), p(out['tol']), p(out['mean']),
+                                  p(out['min']), p(out['max']), p(out['conn']), p(out.get('cen')),
+                                  p(out.get('disp')), p(out.get('p')),
+                                  ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+    ctx.check(rc)
+    return out
+
+
+def conn_perm_test(ctx, dg, Y, perms, observed, log2=True, per_gene=False, want_scores=False, tie_rel=1e-9):
+    """sctda_conn_perm_test.  Y [G, >=Ncells] float64 device; perms int32 device, [n, S]
+    (shared) or [G, n, S] (per_gene); observed [G] float64 device.
+    Returns (exceed int32 [G], ties int32 [G], scores float64 [G, n] or None) on the device."""
+    import ctypes
+    G = int(Y.shape[0])
+    dev = dg.device
+    if per_gene:
+        assert perms.dim() == 3 and perms.shape[0] == G and perms.shape[2] == dg.S
+        n = int(perms.shape[1])
+        stride = n * dg.S
+    else:
+        assert perms.dim() == 2 and perms.shape[1] == dg.S
+        n = int(perms.shape[0])
+        stride = 0
+    assert perms.dtype == torch.int32 and perms.is_contiguous()
+    exceed = torch.empty(G, dtype=torch.int32, device=dev)
+    ties = torch.empty(G, dtype=torch.int32, device=dev)
+    scores = torch.empty((G, n), dtype=torch.float64, device=dev) if want_scores else None
+    p = _lib.ptr
+    rc = ctx.lib.sctda_conn_perm_test(ctx.handle, ctypes.byref(dg.struct), G, p(Y),
+                                      int(Y.stride(0)) if G else dg.Ncells, 1 if log2 else 0, n, p(perms), stride,
+                                      p(observed), float(tie_rel), p(exceed), p(ties), p(scores),
+                                      ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+    ctx.check(rc)
+    return exceed, ties, scores
+
+
+class UnrootedGraph(object):
+    """Topological analysis of non-longitudinal single cell RNA-seq data (ref:781-784)."""
+
+    def __init__(self, name, table, shift=None, log2=True, posgl=False, csv=False, groups=True, device=0):
+        """Same arguments as ref:785; `posgl` is accepted and ignored (layouts are
+        visualisation state); `device` selects the GPU."""
+        self.name = name
+        self.g = networkx.read_gexf(name + '.gexf')                              # ref:801
+        comps = list(networkx.connected_components(self.g))
+        sizes = [len(c) for c in comps]
+        lcc = comps[sizes.index(max(sizes))]                                     # ref:802-804: first largest
+        self.pl = [v for v in self.g.nodes() if v in lcc]                        # ref:805 (file order)
+        self.gl = self.g.subgraph(self.pl)
+        self.adj_csr = scipy.sparse.csr_matrix(
+            networkx.to_scipy_sparse_array(self.g, nodelist=self.pl, dtype=numpy.float64, weight='weight', format='csr'))
+        self.log2 = log2
+        with open(name + '.json', 'r') as h:
+            self.dic = json.load(h)                                              # ref:828-829
+        if groups:
+            with open(name + '.groups.json', 'r') as h:
+                self.dicgroups = json.load(h)
+        else:
+            self.dicgroups = {}
+        names, Y, cell_id, libs, cdr = formats.read_table(table, shift=shift, csv=csv)
+        self.gene_names = names
+        self.gene_row = {}
+        for i, q in enumerate(names):                                            # later duplicates win, ref:876-879
+            self.gene_row[q] = i
+        self.Y = Y
+        self.cellID = numpy.array(cell_id)
+        self.libs = libs
+        self.cdr = cdr
+        samples = []
+        for i in self.pl:                                                        # ref:886-889
+            samples += self.dic[i]
+        self.samples = numpy.array(list(set(samples)))
+        self.device = device
+        self._ctx = None
+        self._dg = {}
+        self._Yd = None
+        self._stats = None
+
+    # -- state -----------------------------------------------------------------------------------
+    @property
+    def dicgenes(self):
+        """ref:880-885: column name -> values over all table rows."""
+        return {q: self.Y[i] for q, i in self.gene_row.items()}
+
+    @property
+    def adj(self):
+        """Dense float64 adjacency of the largest component (ref:806); built on demand."""
+        return self.adj_csr.toarray()
+
+    def _context(self):
+        if self._ctx is None:
+            self._ctx = _lib.context(self.device)
+        return self._ctx
+
+    def _device_graph(self, con=True, ind=1):
+        key = (bool(con), int(ind))
+        if key not in self._dg:
+            if con:
+                nodes, A = self.pl, self.adj_csr
+                samples = self.samples
+            else:
+                nodes = [str(i) for i in self.dic.keys()]
+                A = scipy.sparse.csr_matrix(networkx.to_scipy_sparse_array(
+                    self.g, nodelist=nodes, dtype=numpy.float64, weight='weight', format='csr'))
+                s = []
+                for i in nodes:
+                    s += self.dic[i]
+                samples = numpy.array(list(set(s)))
+            if ind != 1:
+                A = scipy.sparse.csr_matrix(A ** int(ind)) if ind > 0 else scipy.sparse.identity(len(nodes), format='csr')
+            self._dg[key] = DeviceGraph([self.dic[i] for i in nodes], A, samples, self.Y.shape[1], self.device)
+            self._dg[key].nodes = list(nodes)
+        return self._dg[key]
+
+    def _device_table(self):
+        if self._Yd is None:
+            self._Yd = torch.from_numpy(numpy.ascontiguousarray(self.Y)).to(torch.device('cuda', self.device))
+        return self._Yd
+
+    def _rows(self, genes):
+        return torch.as_tensor([self.gene_row[g] for g in genes], dtype=torch.int64,
+                               device=torch.device('cuda', self.device))
+
+    def _all_stats(self):
+        """node statistics of every table column, computed once (log2 mode of the object)."""
+        if self._stats is None:
+            dist = getattr(self, '_dist_dev', None)
+            st = node_stats(self._context(), self._device_graph(), self._device_table(), log2=self.log2, dist=dist)
+            self._stats = {k: v.cpu().numpy() for k, v in st.items()}
+        return self._stats
+
+    # -- per-gene API (ref:893-1051) ---------------------------------------------------------------
+    def get_gene(self, genin, ignore_log=False, con=True):
+        """ref:893-964: (dict node -> normalised node value, normalisation factor)."""
+        if genin is not None and not isinstance(genin, list) and (genin[:4] == 'lib_' or genin[:3] == 'ID_' or genin == '_CDR'):
+            raise NotImplementedError('lib_/ID_/_CDR colourings are visualisation helpers (count_gene), out of scope')
+        genes = genin if isinstance(genin, list) else [genin]
+        dg = self._device_graph(con=con)
+        real = genes
+        if None in genes:                                   # a None resets the accumulation, ref:943-945
+            real = genes[len(genes) - genes[::-1].index(None):]
+        pol = numpy.zeros(dg.V)
+        if real:
+            Y = self._device_table().index_select(0, self._rows(real))
+            st = node_stats(self._context(), dg, Y, log2=(self.log2 and not ignore_log), want_p=True)
+            p = st['p'].cpu().numpy()
+            tol = st['tol'].cpu().numpy()
+            if len(real) == 1:
+                return {k: float(v) for k, v in zip(dg.nodes, p[0])}, float(tol[0])
+            for i in range(len(real)):
+                pol += p[i] * tol[i] if tol[i] > 0.0 else p[i]
+        tot = float(numpy.sum(pol))
+        if tot > 0.0:
+            pol = pol / tot
+        return {k: float(v) for k, v in zip(dg.nodes, pol)}, tot
+
+    def connectivity(self, genis, ind=1):
+        """ref:994-1005."""
+        if isinstance(genis, list) or ind != 1:
+            dicgen = self.get_gene(genis)[0]
+            ex = numpy.array([dicgen[u] for u in self.pl])
+            A = self.adj_csr if ind == 1 else (self.adj_csr ** int(ind))
+            cor = float(len(self.pl)) / float(len(self.pl) - 1)
+            return cor * float(ex @ (A @ ex))
+        return float(self._all_stats()['conn'][self.gene_row[genis]])
+
+    def delta(self, genis, group=None):
+        """ref:1007-1028."""
+        if group is None and not isinstance(genis, list):
+            s = self._all_stats()
+            i = self.gene_row[genis]
+            return float(s['mean'][i]), float(s['min'][i]), float(s['max'][i])
+        dicgen, tot = self.get_gene(genis)
+        if group is not None:
+            per = []
+            if isinstance(group, list):
+                for k in group:
+                    per += self.dicgroups[k]
+                per = list(set(per))
+            else:
+                per = self.dicgroups[group]
+            mi = [dicgen[str(node)] for node in per]
+        else:
+            mi = [dicgen[node] for node in self.pl]
+        if numpy.mean(mi) > 0.0:
+            return numpy.mean(mi) * tot, numpy.min(mi) * tot, numpy.max(mi) * tot
+        return 0.0, 0.0, 0.0
+
+    def expr(self, genis, group=None):
+        """ref:1030-1051."""
+        if group is None:
+            return int(self._all_stats()['expr'][self.gene_row[genis]])
+        per = []
+        if isinstance(group, list):
+            for k in group:
+                per += self.dicgroups[k]
+            per = list(set(per))
+        else:
+            per = self.dicgroups[group]
+        po = []
+        for q in per:
+            po += list(self.dic[str(q)])
+        po = list(set(po))
+        return int(numpy.count_nonzero(self.Y[self.gene_row[genis]][po] > 0.0))
+
+    def connectivity_pvalue(self, genin, n=500):
+        """ref:966-992: n fresh shuffles from the global numpy.random stream."""
+        if genin is None:
+            return 0.0
+        return self.connectivity_pvalues([genin], n=n)[0]
+
+    def connectivity_pvalues(self, genes, n=500, perms=None, batch_bytes=1 << 30, return_ties=False):
+        """p-values of `genes`, in order.  perms=None draws a fresh n x S block per gene from
+        the global numpy.random stream, gene after gene, exactly as ref:1069-1071 consumes it;
+        an int32 array [n, S] is used as one block shared by all genes."""
+        ctx, dg = self._context(), self._device_graph()
+        dev = dg.device
+        stats = self._all_stats()
+        rows = [self.gene_row[g] for g in genes]
+        obs_all = torch.from_numpy(stats['conn'][rows]).to(dev)
+        Yd = self._device_table()
+        pvals = numpy.zeros(len(genes))
+        ties = numpy.zeros(len(genes), dtype=numpy.int64)
+        if len(genes) == 0 or n == 0:
+            return (list(pvals), ties) if return_ties else list(pvals)
+        if perms is not None:
+            pd = torch.as_tensor(numpy.ascontiguousarray(perms, dtype=numpy.int32)).to(dev)
+            ex, ti, _ = conn_perm_test(ctx, dg, Yd.index_select(0, self._rows(genes)), pd, obs_all, log2=self.log2)
+            pvals = ex.cpu().numpy() / float(n)
+            ties = ti.cpu().numpy()
+        else:
+            per = max(1, int(batch_bytes // max(1, 4 * n * dg.S)))
+            for lo in range(0, len(genes), per):
+                hi = min(len(genes), lo + per)
+                block = numpy.empty((hi - lo, n, dg.S), dtype=numpy.int32)
+                for i in range(hi - lo):
+                    block[i] = reference_perm_indices(n, dg.S)
+                pd = torch.from_numpy(block).to(dev)
+                ex, ti, _ = conn_perm_test(ctx, dg, Yd.index_select(0, self._rows(genes[lo:hi])), pd, obs_all[lo:hi],
+                                           log2=self.log2, per_gene=True)
+                pvals[lo:hi] = ex.cpu().numpy() / float(n)
+                ties[lo:hi] = ti.cpu().numpy()
+        return (list(pvals), ties) if return_ties else list(pvals)
+
+    # -- table (ref:1053-1086) -----------------------------------------------------------------------
+    def _table_rows(self, n, filtercells, filterexp, annotation, rooted, perms):
+        s = self._all_stats()
+        lp = sorted(self.gene_row.keys())                                        # ref:1068
+        keep = [gi for gi in lp if s['expr'][self.gene_row[gi]] > filtercells and s['max'][self.gene_row[gi]] > filterexp]
+        pol = self.connectivity_pvalues(keep, n=n, perms=perms)                  # ref:1069-1071
+        por = benjamini_hochberg(pol)                                            # ref:1072
+        header = ['Gene', 'Cells', 'Mean', 'Min', 'Max', 'Connectivity', 'p_value', 'q-value (BH)']
+        if rooted:
+            header += ['Centroid', 'Dispersion']
+        header += sorted(annotation.keys())
+        rows = []
+        for mj, gi in enumerate(keep):                                           # ref:1074-1086
+            i = self.gene_row[gi]
+            row = [gi, int(s['expr'][i]), float(s['mean'][i]), float(s['min'][i]), float(s['max'][i]),
+                   float(s['conn'][i]), float(pol[mj]), float(por[mj])]
+            if rooted:
+                row += self._centroid_from_raw(s['cen'][i], s['disp'][i])
+            for m in sorted(annotation.keys()):
+                row.append('Y' if gi in annotation[m] else 'N')
+            rows.append(row)
+        return header, rows
+
+    def save(self, n=500, filtercells=0, filterexp=0.0, annotation={}, perms=None):
+        """ref:1053-1086: writes name.genes.tsv (the scatter plot of ref:1087-1109 is not
+        produced).  perms: see connectivity_pvalues.  Returns (header, rows)."""
+        header, rows = self._table_rows(n, filtercells, filterexp, annotation, False, perms)
+        formats.write_genes_tsv(self.name + '.genes.tsv', header, rows)
+        return header, rows
+
+
+class RootedGraph(UnrootedGraph):
+    """Longitudinal data: root node, pseudo-time regression, centroid / dispersion columns
+    (ref:1449-1567, 1724-1743, 1879-1914).  Root finding (get_dendrite, ref:1463-1479) is an
+    all-pairs BFS plus one Spearman correlation per node; it is a SURVEY.md §8f "next" row
+    and runs on the host here (scipy), as does the one-off regression."""
+
+    def __init__(self, name, table, rootlane='timepoint', shift=None, log2=True, posgl=False, csv=False,
+                 groups=True, device=0):
+        UnrootedGraph.__init__(self, name, table, shift, log2, posgl, csv, groups, device)
+        self.rootlane = rootlane
+        self.root, self.leaf = self.find_root(self.get_dendrite())               # ref:1536
+        self.dicdis = self.get_distroot(self.root)                               # ref:1562
+        pel2, tol = self.get_gene(self.rootlane, ignore_log=True)                # ref:1563
+        pel = numpy.array([pel2[m] for m in self.pl]) * tol
+        dr = numpy.array([self.dicdis[m] for m in self.pl])
+        self.po = scipy.stats.linregress(pel, dr)                                # ref:1566
+        self._dist_dev = torch.from_numpy(dr.astype(numpy.float64)).to(torch.device('cuda', self.device))
+        self._stats = None
+
+    def _hops(self):
+        if not hasattr(self, '_hop'):
+            self._hop = scipy.sparse.csgraph.shortest_path(self.adj_csr, method='D', unweighted=True)
+        return self._hop
+
+    def get_distroot(self, root):
+        """ref:1454-1461: hop distance of every node of the largest component to `root`."""
+        d = self._hops()[self.pl.index(str(root))]
+        return {k: int(v) for k, v in zip(self.pl, d)}
+
+    def get_dendrite(self):
+        """ref:1463-1479."""
+        daycolor = self.get_gene(self.rootlane, ignore_log=True)[0]
+        day = numpy.array([daycolor[k] for k in self.pl])
+        day = day - day.min()
+        H = self._hops()
+        out = {}
+        for i, k in enumerate(self.pl):
+            sel = H[i] != H[i].max()
+            out[str(k)] = -scipy.stats.spearmanr(day[sel], H[i][sel])[0] if sel.any() else float('nan')
+        return out
+
+    @staticmethod
+    def find_root(dendritem):
+        """ref:1481-1497."""
+        q, q2 = 1000.0, -1000.0
+        ind, ind2 = 0, 0
+        for nn in dendritem.keys():
+            if -2.0 < dendritem[nn] < q:
+                q = dendritem[nn]
+                ind = nn
+            if dendritem[nn] > q2 and dendritem[nn] > -2.0:
+                q2 = dendritem[nn]
+                ind2 = nn
+        return ind, ind2
+
+    def _centroid_from_raw(self, cen, disp):
+        if numpy.isnan(cen):
+            return [None, None]                                                  # ref:1742-1743
+        return [(float(cen) - self.po[1]) / self.po[0], (float(disp) - self.po[1]) / self.po[0]]
+
+    def centroid(self, genin, ignore_log=False):
+        """ref:1724-1743."""
+        if ignore_log or isinstance(genin, list):
+            dicge = self.get_gene(genin, ignore_log=ignore_log)[0]
+            p = numpy.array([dicge[k] for k in self.pl])
+            d = numpy.array([self.dicdis[k] for k in self.pl], dtype=numpy.float64)
+            if p.sum() > 0.0:
+                cen = float((d * p).sum() / p.sum())
+                return self._centroid_from_raw(cen, float(numpy.sqrt((((d - cen) ** 2) * p).sum() / p.sum())))
+            return [None, None]
+        s = self._all_stats()
+        i = self.gene_row[genin]
+        return self._centroid_from_raw(s['cen'][i], s['disp'][i])
+
+    def save(self, n=500, filtercells=0, filterexp=0.0, annotation={}, perms=None):
+        """ref:1879-1914."""
+        header, rows = self._table_rows(n, filtercells, filterexp, annotation, True, perms)
+        formats.write_genes_tsv(self.name + '.genes.tsv', header, rows)
+        return header, rows

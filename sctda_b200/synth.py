@@ -84,3 +84,16 @@ def cover_graph(n_cells, n_nodes, memberships_per_cell=4, chords=None, seed=SEED
             chords -= 1
     edges = numpy.array(sorted(es), dtype=numpy.int64).reshape(-1, 2)
     return members, edges
+
+
+def connectivity_case(n_cells, n_nodes, n_genes, memberships_per_cell=4, seed=SEED, dtype=numpy.float64):
+    """Inputs of the connectivity permutation test at a given scale:
+    returns (members, adj_csr, Y) with Y [n_genes, n_cells] gene-major log2(1+TPM) values,
+    every cell a member of the (connected) graph, adjacency weights 1.0."""
+    import scipy.sparse
+    members, edges = cover_graph(n_cells, n_nodes, memberships_per_cell=memberships_per_cell, seed=seed)
+    i = numpy.concatenate([edges[:, 0], edges[:, 1]])
+    j = numpy.concatenate([edges[:, 1], edges[:, 0]])
+    adj = scipy.sparse.csr_matrix((numpy.ones(i.size), (i, j)), shape=(n_nodes, n_nodes))
+    X, _, _ = expression_matrix(n_cells, n_genes, seed=seed, dtype=dtype)
+    return members, adj, numpy.ascontiguousarray(X.T)

@@ -1,0 +1,275 @@
+"""Parity of the CUDA connectivity path (through the C-ABI, sctda_b200/_lib.py) with the CPU
+oracle (oracle/conn_oracle.py) and with the golden vectors the reference's own source produced
+(tests/golden, oracle/gen_golden.py).  Needs a B200: `pytest -m gpu`.
+
+Tolerances (BASELINE.json north_star): permuted scores within 1e-9 relative, exceed counts /
+p-values exact.  Observed statistics (pure float64, no float32 step): 1e-12 relative.
+A gene whose permuted score falls within 1e-9 (relative) of its observed score is reported by
+the library in `ties`; such a comparison is decided by the last bits of a BLAS summation in the
+reference, so the exactness assertion is made on tie-free genes and the number of tie genes is
+bounded (only degenerate constant genes produce them).
+"""
+import json
+import os
+import shutil
+
+import numpy
+import pytest
+import scipy.sparse
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip('torch')
+
+
+def _gpu():
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    from sctda_b200 import _lib
+    return _lib.context(0)
+
+
+def _oracle_state(members, adj, Y, log2=True):
+    from oracle import conn_oracle as co
+    V = len(members)
+    return co.GraphState([str(k) for k in range(V)], adj.toarray() if scipy.sparse.issparse(adj) else adj,
+                         {str(k): [int(c) for c in members[k]] for k in range(V)},
+                         {'g%d' % i: Y[i] for i in range(Y.shape[0])}, log2=log2)
+
+
+def _random_case(seed, n_cells, n_nodes, n_genes, ragged=False, weights=False):
+    """Random connected cover: ring + chords; optionally ragged node sizes (1..), unsorted
+    member lists, non-unit edge weights and cells missing from the graph."""
+    from sctda_b200 import synth
+    rng = numpy.random.RandomState(seed)
+    members, adj, Y = synth.connectivity_case(n_cells, n_nodes, n_genes, seed=seed)
+    if ragged:
+        members = [rng.permutation(m)[:max(1, rng.randint(1, len(m) + 1))] for m in members]
+        members[0] = members[0][:1]
+    if weights:
+        adj = adj.tocoo()
+        w = rng.uniform(0.5, 2.0, adj.nnz)
+        adj = scipy.sparse.coo_matrix((w, (adj.row, adj.col)), shape=adj.shape)
+        adj = ((adj + adj.T) * 0.5).tocsr()
+    Y[0] = 0.0                       # all-zero gene: tol = 0
+    Y[1] = 2.5                       # constant gene: every permuted score equals the observed one (ties)
+    if n_genes > 2:
+        Y[2] = 0.0
+        Y[2, members[0][0]] = 6.0    # single expressing cell
+    return members, adj.tocsr(), Y
+
+
+@pytest.mark.parametrize('log2', [True, False])
+@pytest.mark.parametrize('shape', [(400, 40, 37, 48, False, False), (900, 150, 70, 33, True, True),
+                                   (64, 2, 5, 16, False, False)])
+def test_perm_test_matches_oracle(log2, shape):
+    from oracle import conn_oracle as co
+    from sctda_b200 import graph
+    ctx = _gpu()
+    n_cells, n_nodes, n_genes, n, ragged, weights = shape
+    members, adj, Y = _random_case(17 + n_nodes, n_cells, n_nodes, n_genes, ragged, weights)
+    if n_nodes == 2:
+        adj = scipy.sparse.csr_matrix(numpy.array([[0.0, 1.0], [1.0, 0.0]]))
+    st = _oracle_state(members, adj, Y, log2=log2)
+    dg = graph.DeviceGraph(members, adj, st.samples, n_cells, 0)
+    Yd = torch.from_numpy(Y).cuda()
+    stats = graph.node_stats(ctx, dg, Yd, log2=log2, want_p=True)
+    rng = numpy.random.RandomState(99)
+    shared = co.perm_indices(n, dg.S, rng)
+    per_gene = numpy.stack([co.perm_indices(n, dg.S, rng) for _ in range(n_genes)])
+    ex_s, ti_s, sc_s = graph.conn_perm_test(ctx, dg, Yd, torch.from_numpy(shared).cuda(), stats['conn'], log2=log2,
+                                            want_scores=True)
+    ex_g, ti_g, sc_g = graph.conn_perm_test(ctx, dg, Yd, torch.from_numpy(per_gene).cuda(), stats['conn'], log2=log2,
+                                            per_gene=True, want_scores=True)
+    torch.cuda.synchronize()
+    tie_genes = 0
+    for i in range(n_genes):
+        gi = 'g%d' % i
+        # observed statistics
+        dic, tol = co.get_gene(st, gi)
+        assert stats['tol'][i].item() == pytest.approx(tol, rel=1e-12, abs=0)
+        numpy.testing.assert_allclose(stats['p'][i].cpu().numpy(), [dic[k] for k in st.pl], rtol=1e-12, atol=0)
+        obs = co.connectivity(st, gi)
+        assert stats['conn'][i].item() == pytest.approx(obs, rel=1e-12, abs=0)
+        numpy.testing.assert_allclose([stats[k][i].item() for k in ('mean', 'min', 'max')], co.delta(st, gi),
+                                      rtol=1e-12, atol=0)
+        assert stats['expr'][i].item() == co.expr(st, gi)
+        # permuted scores and exceed counts
+        for ex, ti, sc, perms in ((ex_s, ti_s, sc_s, shared), (ex_g, ti_g, sc_g, per_gene[i])):
+            with numpy.errstate(invalid='ignore', divide='ignore'):
+                ref = co.permuted_scores(st, gi, n=n, perms=perms)
+            got = sc[i].cpu().numpy()
+            if tol > 0.0:
+                numpy.testing.assert_allclose(got, ref, rtol=1e-9, atol=0)
+            else:
+                assert numpy.isnan(got).all() and numpy.isnan(ref).all()
+            if ti[i].item() == 0:
+                assert ex[i].item() == int(numpy.sum(ref > obs))
+            else:
+                tie_genes += 1
+                band = numpy.abs(ref - obs) <= 2e-9 * abs(obs)
+                lo = int(numpy.sum((ref > obs) & ~band))
+                assert lo <= ex[i].item() <= lo + int(band.sum())
+    assert tie_genes <= 2 * 1          # only the constant gene (two permutation sources)
+
+
+@pytest.mark.parametrize('name', ['unrooted_a', 'rooted_b'])
+def test_golden_reference_vectors(golden_dir, tmp_path, name):
+    """The product classes on the files the reference itself was run on (gen_golden.py)."""
+    _gpu()
+    from sctda_b200 import graph
+    for ext in ('.gexf', '.json', '.all.tsv'):
+        shutil.copy(os.path.join(golden_dir, name + ext), str(tmp_path / (name + ext)))
+    with open(os.path.join(golden_dir, name + '.ref.json')) as f:
+        ref = json.load(f)
+    prefix = str(tmp_path / name)
+    rooted = ref['rooted']
+    if rooted:
+        c = graph.RootedGraph(prefix, prefix + '.all.tsv', groups=False)
+        assert (str(c.root), str(c.leaf)) == (ref['root'], ref['leaf'])
+        assert {k: int(v) for k, v in c.dicdis.items()} == ref['dicdis']
+        assert [float(c.po[0]), float(c.po[1])] == pytest.approx(ref['po'], rel=1e-12)
+        den = c.get_dendrite()
+        for k, v in ref['dendrite'].items():
+            assert den[k] == pytest.approx(v, rel=1e-9, abs=1e-12, nan_ok=True)
+    else:
+        c = graph.UnrootedGraph(prefix, prefix + '.all.tsv', groups=False)
+    assert sorted(c.pl) == sorted(ref['pl'])
+    assert [int(x) for x in c.samples] == ref['samples']
+    n = ref['n_perm']
+    order = [ref['pl'].index(k) for k in c.pl]
+    for gi, r in ref['per_gene'].items():
+        dic, tol = c.get_gene(gi)
+        assert tol == pytest.approx(r['tol'], rel=1e-12, abs=0)
+        numpy.testing.assert_allclose([dic[k] for k in c.pl], numpy.array(r['p_nodes'])[order], rtol=1e-12, atol=0)
+        assert c.connectivity(gi) == pytest.approx(r['connectivity'], rel=1e-12, abs=0)
+        numpy.testing.assert_allclose(c.delta(gi), r['delta'], rtol=1e-12, atol=0)
+        assert c.expr(gi) == r['expr']
+        numpy.random.seed(ref['seed'] + 7)
+        pv, ties = c.connectivity_pvalues([gi], n=n, return_ties=True)
+        if ties[0] == 0:
+            assert pv[0] == r['p_value']
+        if rooted:
+            cen = c.centroid(gi)
+            if r['centroid'][0] is None:
+                assert cen == [None, None]
+            else:
+                numpy.testing.assert_allclose(cen, r['centroid'], rtol=1e-10)
+    # the table writer, RNG stream consumed gene by gene from `seed` (ref:1068-1071)
+    genes = sorted(c.gene_row.keys())
+    numpy.random.seed(ref['seed'])
+    header, rows = c.save(n=n, annotation={'setA': genes[3:9], 'setB': genes[5:6]})
+    with open(os.path.join(golden_dir, name + '.ref.genes.tsv')) as f:
+        gold = [l[:-1].split('\t') for l in f]
+    with open(prefix + '.genes.tsv') as f:
+        mine = [l[:-1].split('\t') for l in f]
+    assert mine[0] == gold[0] == header
+    assert len(mine) == len(gold)
+    _, ties = (None, None)
+    for a, b in zip(mine[1:], gold[1:]):
+        assert a[0] == b[0] and a[1] == b[1]
+        for j in range(2, len(gold[0])):
+            if gold[0][j] in ('setA', 'setB') or b[j] == 'None':
+                assert a[j] == b[j]
+            elif gold[0][j] in ('p_value', 'q-value (BH)'):
+                continue
+            else:
+                assert float(a[j]) == pytest.approx(float(b[j]), rel=6e-12, abs=1e-300)
+    # p-values: exact wherever no permuted score ties with the observed one
+    numpy.random.seed(ref['seed'])
+    keep = [r[0] for r in rows]
+    pv, ties = c.connectivity_pvalues(keep, n=n, return_ties=True)
+    n_tied = 0
+    for a, b, p, t in zip(mine[1:], gold[1:], pv, ties):
+        if t == 0:
+            assert float(a[6]) == float(b[6]) == p
+        else:
+            n_tied += 1
+    assert n_tied <= 1                 # G000 is constant (gen_golden.write_case)
+    if n_tied == 0:
+        for a, b in zip(mine[1:], gold[1:]):
+            assert float(a[7]) == pytest.approx(float(b[7]), rel=6e-12)
+
+
+def test_invariants_at_scale():
+    """Size-independent properties at a size the oracle cannot reach."""
+    ctx = _gpu()
+    from sctda_b200 import graph, synth
+    n_cells, n_nodes, n_genes, n = 20000, 2000, 96, 64
+    members, adj, Y = synth.connectivity_case(n_cells, n_nodes, n_genes, seed=5)
+    Yd = torch.from_numpy(Y).cuda()
+    dg = graph.DeviceGraph(members, adj, numpy.arange(n_cells), n_cells, 0)
+    rng = numpy.random.RandomState(1)
+    perms = numpy.stack([rng.permutation(n_cells) for _ in range(n)]).astype(numpy.int32)
+    perms[0] = numpy.arange(n_cells)             # identity permutation first
+    pd = torch.from_numpy(perms).cuda()
+    # (1) p * n is an integer in [0, n]; scores finite; identity permutation reproduces the observed
+    #     score up to the float32 rounding of ref:972 (linear mode: <= 1e-6 relative)
+    st = graph.node_stats(ctx, dg, Yd, log2=False)
+    ex, ti, sc = graph.conn_perm_test(ctx, dg, Yd, pd, st['conn'], log2=False, want_scores=True)
+    ex = ex.cpu().numpy()
+    sc = sc.cpu().numpy()
+    obs = st['conn'].cpu().numpy()
+    assert ((ex >= 0) & (ex <= n)).all()
+    assert numpy.isfinite(sc).all()
+    numpy.testing.assert_allclose(sc[:, 0], obs, rtol=1e-6)
+    numpy.testing.assert_array_equal(ex, (sc > obs[:, None]).sum(axis=1))
+    # (2) invariance under node relabelling (<= 1e-12): reverse the node order
+    rev = list(range(n_nodes))[::-1]
+    P = scipy.sparse.csr_matrix((numpy.ones(n_nodes), (numpy.arange(n_nodes), rev)), shape=(n_nodes, n_nodes))
+    dg2 = graph.DeviceGraph([members[k] for k in rev], (P @ adj @ P.T).tocsr(), numpy.arange(n_cells), n_cells, 0)
+    st2 = graph.node_stats(ctx, dg2, Yd, log2=False)
+    _, _, sc2 = graph.conn_perm_test(ctx, dg2, Yd, pd, st2['conn'], log2=False, want_scores=True)
+    numpy.testing.assert_allclose(st2['conn'].cpu().numpy(), obs, rtol=1e-12)
+    numpy.testing.assert_allclose(sc2.cpu().numpy(), sc, rtol=1e-12)
+    # (3) a uniform p has connectivity V/(V-1) * 2E/V^2: a constant gene in linear mode
+    Yc = torch.full((1, n_cells), 3.0, dtype=torch.float64, device='cuda')
+    stc = graph.node_stats(ctx, dg, Yc, log2=False)
+    E2 = adj.nnz                                  # 2E
+    assert stc['conn'][0].item() == pytest.approx(n_nodes / (n_nodes - 1.0) * E2 / n_nodes ** 2, rel=1e-12)
+    # (4) shared block == the same block replicated per gene
+    few = 40
+    rep = pd[:8].unsqueeze(0).repeat(few, 1, 1).contiguous()
+    stl = graph.node_stats(ctx, dg, Yd[:few], log2=True)
+    exa, _, sca = graph.conn_perm_test(ctx, dg, Yd[:few], pd[:8].contiguous(), stl['conn'], want_scores=True)
+    exb, _, scb = graph.conn_perm_test(ctx, dg, Yd[:few], rep, stl['conn'], per_gene=True, want_scores=True)
+    assert torch.equal(exa, exb) and torch.equal(sca, scb)
+
+
+def test_edge_cases_and_errors():
+    ctx = _gpu()
+    import ctypes
+    from sctda_b200 import _lib, graph, synth
+    members, adj, Y = synth.connectivity_case(200, 20, 3, seed=9)
+    dg = graph.DeviceGraph(members, adj, numpy.arange(200), 200, 0)
+    Yd = torch.from_numpy(Y).cuda()
+    st = graph.node_stats(ctx, dg, Yd)
+    # n = 0 permutations: counts are zero
+    ex, ti, _ = graph.conn_perm_test(ctx, dg, Yd, torch.zeros((0, 200), dtype=torch.int32, device='cuda'), st['conn'])
+    assert ex.sum().item() == 0
+    # G = 0 genes
+    ex, ti, _ = graph.conn_perm_test(ctx, dg, Yd[:0], torch.zeros((4, 200), dtype=torch.int32, device='cuda'),
+                                     st['conn'][:0])
+    assert ex.numel() == 0
+    # a graph with a single node is rejected (V/(V-1)), with a message
+    g1 = _lib.Graph(V=1, S=200, Ncells=200, reserved=0, d_node_off=dg.node_off.data_ptr(),
+                    d_node_cols=dg.node_cols.data_ptr(), d_adj_off=dg.adj_off.data_ptr(),
+                    d_adj_idx=dg.adj_idx.data_ptr(), d_adj_w=dg.adj_w.data_ptr(), d_samples=dg.samples.data_ptr())
+    rc = ctx.lib.sctda_node_stats(ctx.handle, ctypes.byref(g1), 3, _lib.ptr(Yd), 200, 1, None, None, None, None, None,
+                                  None, None, None, None, None, None)
+    assert rc == -1 and b'V >= 2' in ctx.lib.sctda_last_error(ctx.handle)
+    # missing required pointer
+    rc = ctx.lib.sctda_conn_perm_test(ctx.handle, ctypes.byref(dg.struct), 3, _lib.ptr(Yd), 200, 1, 4, None, 0,
+                                      _lib.ptr(st['conn']), 0.0, None, None, None, None)
+    assert rc == -1
+    # cells outside the largest component: samples is a strict subset of the table rows
+    sub = numpy.arange(0, 200, 2)
+    members2 = [numpy.array([c for c in m if c % 2 == 0] or [0]) for m in members]
+    dg2 = graph.DeviceGraph(members2, adj, sub, 200, 0)
+    from oracle import conn_oracle as co
+    state = co.GraphState([str(k) for k in range(20)], adj.toarray(),
+                          {str(k): [int(c) for c in members2[k]] for k in range(20)}, {'g0': Y[0]})
+    assert [int(x) for x in state.samples] == [int(x) for x in sub]
+    st2 = graph.node_stats(ctx, dg2, Yd[:1])
+    assert st2['conn'][0].item() == pytest.approx(co.connectivity(state, 'g0'), rel=1e-12)
+    assert st2['expr'][0].item() == co.expr(state, 'g0')      # expr counts ALL table rows (ref:1050)

@@ -1,0 +1,113 @@
+"""CPU-side checks: the C-ABI library builds, loads and exports every symbol the header
+declares (no compute calls); host logic (formats, BH, permutation source) against the oracle
+and the golden vectors."""
+import ctypes
+import json
+import os
+import re
+
+import numpy
+import pytest
+
+from oracle import conn_oracle as co
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope='module')
+def lib_path():
+    from sctda_b200 import build
+    return build.build()
+
+
+def test_library_exports_every_declared_symbol(lib_path):
+    from sctda_b200 import _lib
+    with open(os.path.join(ROOT, 'include', 'sctda_b200.h')) as f:
+        text = re.sub(r'/\*.*?\*/', '', f.read(), flags=re.S)
+    declared = set(re.findall(r'\b(sctda_[a-z0-9_]+)\s*\(', text))
+    assert declared, 'no declarations found'
+    lib = ctypes.CDLL(lib_path)
+    for name in declared:
+        assert hasattr(lib, name), name
+    # the ctypes binding covers exactly the declared surface
+    assert declared == set(_lib.SIGNATURES.keys())
+    loaded = _lib.load()
+    assert loaded.sctda_abi_version() == 1
+
+
+def test_no_gpu_means_loud_failure(lib_path):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    from sctda_b200 import _lib
+    with pytest.raises(_lib.SctdaError):
+        _lib.Context(0)
+
+
+def test_product_does_not_import_the_oracle():
+    pkg = os.path.join(ROOT, 'sctda_b200')
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith(('.py', '.cu', '.cuh', '.h')):
+                with open(os.path.join(dirpath, fn)) as f:
+                    src = f.read()
+                assert not re.search(r'^\s*(from|import)\s+oracle\b', src, flags=re.M), fn
+
+
+def test_benjamini_hochberg_matches_reference_vectors(golden_dir):
+    from sctda_b200 import graph
+    with open(os.path.join(golden_dir, 'bh.ref.json')) as f:
+        d = json.load(f)
+    assert graph.benjamini_hochberg(d['p']) == d['q']
+    rs = numpy.random.RandomState(0)
+    for n in (1, 2, 7, 100):
+        p = list(numpy.round(rs.rand(n), 2))
+        assert graph.benjamini_hochberg(p) == co.benjamini_hochberg(p)
+    assert graph.benjamini_hochberg([]) == []
+
+
+def test_permutation_source_is_the_reference_stream():
+    from sctda_b200 import graph
+    numpy.random.seed(4242)
+    a = graph.reference_perm_indices(5, 37)
+    numpy.random.seed(4242)
+    x = numpy.tile(numpy.arange(37) * 1.5, (5, 1))
+    for row in x:                       # ref:976
+        numpy.random.shuffle(row)
+    numpy.testing.assert_array_equal(x, (numpy.arange(37) * 1.5)[a])
+    assert sorted(a[3]) == list(range(37))
+
+
+@pytest.mark.parametrize('name', ['unrooted_a', 'rooted_b'])
+def test_read_table_matches_oracle_parse(golden_dir, name):
+    from sctda_b200 import formats
+    path = os.path.join(golden_dir, name + '.all.tsv')
+    names, Y, cell_id, libs, cdr = formats.read_table(path)
+    dicgenes, cell_id2, libs2, cdr2 = co.parse_table(path)
+    assert names == list(dicgenes.keys())
+    for i, q in enumerate(names):
+        numpy.testing.assert_array_equal(Y[i], dicgenes[q])
+    assert list(cell_id) == cell_id2 and list(libs) == libs2
+    numpy.testing.assert_array_equal(cdr, cdr2)
+    # shift variants (ref:875-878)
+    n3, Y3, _, _, _ = formats.read_table(path, shift=3)
+    assert n3 == names[3:]
+    numpy.testing.assert_array_equal(Y3, Y[3:])
+    n4, Y4, _, _, _ = formats.read_table(path, shift=[3, 5])
+    assert n4 == [names[3], names[5]]
+
+
+def test_py2_str_and_writers(tmp_path):
+    from sctda_b200 import formats
+    for v in (0.0, 0.904, 0.02489375434321234, 710, 1e-20, 3.0, None, 1e16, 123456789012.0, float('nan')):
+        assert formats.py2_str(v) == co.py2_str(v)
+    import networkx
+    p = str(tmp_path / 'g')
+    formats.write_gexf(p + '.gexf', 4, [(0, 1), (1, 3)])
+    g = networkx.read_gexf(p + '.gexf')
+    assert sorted(g.nodes()) == ['0', '1', '2', '3']
+    assert sorted(tuple(sorted(e)) for e in g.edges()) == [('0', '1'), ('1', '3')]
+    assert all(d['weight'] == 1.0 for _, _, d in g.edges(data=True))
+    formats.write_mapper_json(p + '.json', [[3, 1], numpy.array([2])])
+    with open(p + '.json') as f:
+        assert json.load(f) == {'0': [3, 1], '1': [2]}
