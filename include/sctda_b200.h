@@ -60,6 +60,13 @@ int64_t sctda_workspace_bytes(const sctda_ctx* ctx);
  * (bench.py reports the per-step difference as "gpu_launches"). */
 int64_t sctda_launch_count(const sctda_ctx* ctx);
 
+/* Measurement aid (bench.py "roofline"): when enabled, every hot-path call brackets its
+ * DOMINANT kernel (conn_perm_kernel for sctda_conn_perm_test) with CUDA events on the
+ * caller's stream.  sctda_last_kernel_ms waits for that kernel to finish (host sync on
+ * the event) and returns its duration in milliseconds. */
+int32_t sctda_set_kernel_timing(sctda_ctx* ctx, int32_t enabled);
+int32_t sctda_last_kernel_ms(sctda_ctx* ctx, float* out_ms);
+
 /* ---- hot path (b): connectivity permutation test ------------------------------------------- */
 
 /*

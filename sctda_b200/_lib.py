@@ -40,6 +40,8 @@ SIGNATURES = {
     'sctda_last_error': (ctypes.c_char_p, [c_ptr]),
     'sctda_workspace_bytes': (c_i64, [c_ptr]),
     'sctda_launch_count': (c_i64, [c_ptr]),
+    'sctda_set_kernel_timing': (c_i32, [c_ptr, c_i32]),
+    'sctda_last_kernel_ms': (c_i32, [c_ptr, ctypes.POINTER(ctypes.c_float)]),
     'sctda_node_stats': (c_i32, [c_ptr, ctypes.POINTER(Graph), c_i32, c_ptr, c_i64, c_i32, c_ptr,
                                  c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     'sctda_conn_perm_test': (c_i32, [c_ptr, ctypes.POINTER(Graph), c_i32, c_ptr, c_i64, c_i32,
@@ -91,6 +93,14 @@ class Context(object):
 
     def launch_count(self):
         return int(self.lib.sctda_launch_count(self.handle))
+
+    def set_kernel_timing(self, enabled=True):
+        self.check(self.lib.sctda_set_kernel_timing(self.handle, 1 if enabled else 0))
+
+    def last_kernel_ms(self):
+        ms = ctypes.c_float()
+        self.check(self.lib.sctda_last_kernel_ms(self.handle, ctypes.byref(ms)))
+        return float(ms.value)
 
     def workspace_bytes(self):
         return int(self.lib.sctda_workspace_bytes(self.handle))

@@ -17,6 +17,9 @@ struct sctda_ctx {
     void* slot_ptr[SCTDA_NUM_SLOTS];     // grow-only device workspace, one buffer per slot
     size_t slot_bytes[SCTDA_NUM_SLOTS];
     int64_t launches;
+    int timing;                          // sctda_set_kernel_timing
+    int timed;                           // events recorded at least once
+    cudaEvent_t ev0, ev1;
 };
 
 // Workspace slots (one live use per call; calls on one context are serialised by contract).
@@ -85,3 +88,7 @@ static inline void* sctda_ws(sctda_ctx* ctx, int slot, size_t bytes) {
 }
 
 static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// Brackets the dominant kernel of a call with events when timing is on (see sctda_set_kernel_timing).
+#define SCTDA_TIME_BEGIN(ctx, st) do { if ((ctx)->timing) cudaEventRecord((ctx)->ev0, st); } while (0)
+#define SCTDA_TIME_END(ctx, st) do { if ((ctx)->timing) { cudaEventRecord((ctx)->ev1, st); (ctx)->timed = 1; } } while (0)

@@ -426,8 +426,10 @@ extern "C" int32_t sctda_conn_perm_test(sctda_ctx* ctx, const sctda_graph* gr, i
     const int grid = (int)grid64;
     a.pm = (float*)sctda_ws(ctx, WS_PM, (size_t)grid * gr->V * kLanes * sizeof(float));
     if (!a.pm) return SCTDA_ERR_NOMEM;
+    SCTDA_TIME_BEGIN(ctx, st);
     if (perm_gene_stride == 0) conn_perm_kernel<NW, true><<<grid, NW * 32, 0, st>>>(a);
     else conn_perm_kernel<NW, false><<<grid, NW * 32, 0, st>>>(a);
+    SCTDA_TIME_END(ctx, st);
     SCTDA_LAUNCH_CHECK(ctx, "conn_perm_kernel");
     return SCTDA_OK;
 }

@@ -38,6 +38,8 @@ extern "C" int32_t sctda_ctx_destroy(sctda_ctx* ctx) {
     cudaDeviceSynchronize();
     for (int i = 0; i < SCTDA_NUM_SLOTS; ++i)
         if (ctx->slot_ptr[i]) cudaFree(ctx->slot_ptr[i]);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     free(ctx);
     return SCTDA_OK;
 }
@@ -52,3 +54,22 @@ extern "C" int64_t sctda_workspace_bytes(const sctda_ctx* ctx) {
 }
 
 extern "C" int64_t sctda_launch_count(const sctda_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int32_t sctda_set_kernel_timing(sctda_ctx* ctx, int32_t enabled) {
+    if (!ctx) return SCTDA_ERR_INVALID;
+    if (enabled && !ctx->ev0) {
+        SCTDA_CUDA(ctx, cudaSetDevice(ctx->device));
+        SCTDA_CUDA(ctx, cudaEventCreate(&ctx->ev0));
+        SCTDA_CUDA(ctx, cudaEventCreate(&ctx->ev1));
+    }
+    ctx->timing = enabled ? 1 : 0;
+    return SCTDA_OK;
+}
+
+extern "C" int32_t sctda_last_kernel_ms(sctda_ctx* ctx, float* out_ms) {
+    if (!ctx || !out_ms) return SCTDA_ERR_INVALID;
+    if (!ctx->timed) return sctda_fail(ctx, SCTDA_ERR_INVALID, "no timed kernel yet (sctda_set_kernel_timing)%s");
+    SCTDA_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
+    SCTDA_CUDA(ctx, cudaEventElapsedTime(out_ms, ctx->ev0, ctx->ev1));
+    return SCTDA_OK;
+}

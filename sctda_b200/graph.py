@@ -141,6 +141,22 @@ def conn_perm_test(ctx, dg, Y, perms, observed, log2=True, per_gene=False, want_
     return exceed, ties, scores
 
 
+def conn_perm_test_host(ctx, dg, Y_host, perms_host, observed_host, log2=True):
+    """The permutation test on HOST buffers (pinned torch tensors or numpy arrays): copies the
+    table, the shared permutation block and the observed scores to the device, runs
+    sctda_conn_perm_test and returns the exceed counts as a host int32 tensor.  This is the
+    call behind UnrootedGraph.connectivity_pvalues and bench.py's end-to-end number."""
+    dev = dg.device
+    Yd = torch.as_tensor(Y_host).to(dev, non_blocking=True)
+    pd = torch.as_tensor(perms_host).to(dev, non_blocking=True)
+    od = torch.as_tensor(observed_host).to(dev, non_blocking=True)
+    ex, _, _ = conn_perm_test(ctx, dg, Yd, pd, od, log2=log2, per_gene=(pd.dim() == 3))
+    out = torch.empty(ex.shape, dtype=ex.dtype, pin_memory=True)
+    out.copy_(ex, non_blocking=True)
+    torch.cuda.current_stream(dev).synchronize()
+    return out
+
+
 class UnrootedGraph(object):
     """Topological analysis of non-longitudinal single cell RNA-seq data (ref:781-784)."""
 

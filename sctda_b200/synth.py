@@ -97,3 +97,81 @@ def connectivity_case(n_cells, n_nodes, n_genes, memberships_per_cell=4, seed=SE
     adj = scipy.sparse.csr_matrix((numpy.ones(i.size), (i, j)), shape=(n_nodes, n_nodes))
     X, _, _ = expression_matrix(n_cells, n_genes, seed=seed, dtype=dtype)
     return members, adj, numpy.ascontiguousarray(X.T)
+
+
+def _gene_params(rng, n_genes):
+    amp = rng.lognormal(3.0, 1.0, n_genes)
+    tau = rng.uniform(0.0, 1.0, n_genes)
+    sig = rng.uniform(0.05, 0.3, n_genes)
+    mask = rng.randint(1, 8, n_genes)
+    return amp, tau, sig, mask
+
+
+def _cell_latents(n_cells, seed):
+    rng = numpy.random.RandomState(seed)
+    t = rng.uniform(0.0, 1.0, n_cells)
+    branch = numpy.where(t > 0.5, rng.randint(0, 3, n_cells), 0)
+    return t, branch
+
+
+def expression_genes_numpy(n_genes, n_cells, seed=SEED, gene_offset=0):
+    """Gene-major [n_genes, n_cells] float64 table of the same trajectory model as
+    expression_matrix, generated gene block by gene block (no per-cell TPM normalisation:
+    values = log2(1 + 50 * count)), 60-80 % zeros.  Host generator for the CPU arm."""
+    t, branch = _cell_latents(n_cells, seed)
+    out = numpy.empty((n_genes, n_cells), dtype=numpy.float64)
+    blk = 256
+    for lo in range(0, n_genes, blk):
+        hi = min(n_genes, lo + blk)
+        rng = numpy.random.RandomState((seed + 7919 * ((gene_offset + lo) // blk + 1)) % (2 ** 31))
+        amp, tau, sig, mask = _gene_params(rng, hi - lo)
+        active = ((mask[:, None] >> branch[None, :]) & 1).astype(numpy.float64)
+        mu = 0.15 * amp[:, None] * numpy.exp(-(t[None, :] - tau[:, None]) ** 2 / (2.0 * sig[:, None] ** 2)) * active
+        lam = rng.gamma(shape=2.0, scale=0.5 * mu + 1e-300)
+        out[lo:hi] = numpy.log2(1.0 + 50.0 * rng.poisson(lam))
+    return out
+
+
+def expression_genes_torch(n_genes, n_cells, seed=SEED, device='cuda', gene_offset=0):
+    """Device generator of the same model (bench.py): gene-major float64 [n_genes, n_cells].
+    Gene g's parameters depend only on (seed, gene_offset + g), so shards of a gene range are
+    consistent whatever the number of ranks; the Poisson draws come from torch's generator."""
+    import torch
+    t, branch = _cell_latents(n_cells, seed)
+    dev = torch.device(device)
+    td = torch.from_numpy(t).to(dev)
+    bd = torch.from_numpy(branch.astype(numpy.int64)).to(dev)
+    out = torch.empty((n_genes, n_cells), dtype=torch.float64, device=dev)
+    gen = torch.Generator(device=dev)
+    blk = 256
+    lo = 0
+    while lo < n_genes:
+        g0 = gene_offset + lo
+        hi = min(n_genes, lo + blk - (g0 % blk))
+        bidx = g0 // blk
+        rng = numpy.random.RandomState((seed + 7919 * (bidx + 1)) % (2 ** 31))
+        amp, tau, sig, mask = _gene_params(rng, blk)
+        sl = slice(g0 % blk, g0 % blk + (hi - lo))
+        amp, tau, sig = [torch.from_numpy(x[sl]).to(dev) for x in (amp, tau, sig)]
+        mk = torch.from_numpy(mask[sl].astype(numpy.int64)).to(dev)
+        active = ((mk[:, None] >> bd[None, :]) & 1).to(torch.float64)
+        mu = 0.15 * amp[:, None] * torch.exp(-(td[None, :] - tau[:, None]) ** 2 / (2.0 * sig[:, None] ** 2)) * active
+        gen.manual_seed(int(seed + 104729 * (bidx + 1) + (g0 % blk)))
+        lam = torch._standard_gamma(torch.full_like(mu, 2.0), generator=gen) * (0.5 * mu)
+        out[lo:hi] = torch.log2(1.0 + 50.0 * torch.poisson(lam, generator=gen))
+        lo = hi
+    return out
+
+
+def permutation_block_torch(n, S, seed=SEED, device='cuda'):
+    """[n, S] int32: n uniformly random permutations of 0..S-1 (argsort of uniform keys)."""
+    import torch
+    dev = torch.device(device)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(int(seed))
+    out = torch.empty((n, S), dtype=torch.int32, device=dev)
+    step = max(1, (1 << 24) // max(S, 1))
+    for lo in range(0, n, step):
+        hi = min(n, lo + step)
+        out[lo:hi] = torch.rand((hi - lo, S), generator=gen, device=dev).argsort(dim=1).to(torch.int32)
+    return out
