@@ -80,6 +80,10 @@ int32_t sctda_last_kernel_ms(sctda_ctx* ctx, float* out_ms);
  *   d_adj_off    [V+1]   CSR of self.adj (ref:806), rows in self.pl order
  *   d_adj_idx    [nnz]   column (node) indices
  *   d_adj_w      [nnz]   float64 edge weights
+ *                        The adjacency enters only through the quadratic form p'Ap
+ *                        (ref:989, 1003): any A' with A' + A'^T == A + A^T gives the same
+ *                        statistic, so callers may pass the upper-triangular form
+ *                        triu(A + A^T, 1) + diag(A) and halve the sparse work.
  *   S            len(self.samples); d_samples [S] = self.samples (table row of each column)
  *   Ncells       rows of the expression table
  */
@@ -148,6 +152,14 @@ int32_t sctda_conn_perm_test(sctda_ctx* ctx, const sctda_graph* graph,
                              const double* d_observed, double tie_rel,
                              int32_t* d_exceed, int32_t* d_ties, double* d_scores,
                              void* stream);
+
+/*
+ * Diagnostic: the permutation kernel divides with a reciprocal and one fused correction step
+ * instead of the generic IEEE division; this runs n_trials pseudo-random comparisons of the
+ * two on the device (numerators 0 and 2^-24..2^40, divisors 1..8192 and 0.693147) and returns
+ * the number of results that differ in any bit (expected: 0).  Synchronises the host.
+ */
+int32_t sctda_selftest_div(sctda_ctx* ctx, int64_t n_trials, int64_t* out_mismatches);
 
 #ifdef __cplusplus
 }

@@ -42,6 +42,7 @@ SIGNATURES = {
     'sctda_launch_count': (c_i64, [c_ptr]),
     'sctda_set_kernel_timing': (c_i32, [c_ptr, c_i32]),
     'sctda_last_kernel_ms': (c_i32, [c_ptr, ctypes.POINTER(ctypes.c_float)]),
+    'sctda_selftest_div': (c_i32, [c_ptr, c_i64, ctypes.POINTER(c_i64)]),
     'sctda_node_stats': (c_i32, [c_ptr, ctypes.POINTER(Graph), c_i32, c_ptr, c_i64, c_i32, c_ptr,
                                  c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     'sctda_conn_perm_test': (c_i32, [c_ptr, ctypes.POINTER(Graph), c_i32, c_ptr, c_i64, c_i32,

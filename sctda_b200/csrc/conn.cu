@@ -77,37 +77,62 @@ __global__ void __launch_bounds__(256) expr_count_kernel(const double* __restric
     if (lane == 0) out[warp] = c;
 }
 
+// a / b for finite a, b > 0 given rb = RN(1/b): one Markstein correction step.  With a
+// correctly rounded reciprocal and fused multiply-adds this returns the correctly rounded
+// quotient RN(a/b), i.e. the same bits as the IEEE division the reference performs, without the
+// slow path the generic double division takes for a zero numerator (checked exhaustively for
+// the divisors used here by sctda_selftest_div).
+__device__ __forceinline__ double div_rn(double a, double b, double rb) {
+    double q = a * rb;
+    double r = fma(-q, b, a);
+    return fma(r, rb, q);
+}
+
+// Where the permutation of the current (gene tile, permutation) item is read from.
+enum PermKind {
+    PERM_NONE = 0,        // identity (observed statistics)
+    PERM_GLOBAL = 1,      // one row shared by the 32 lanes, gathered from global memory
+    PERM_SMEM = 2,        // one row shared by the 32 lanes, staged in shared memory by cp.async
+    PERM_PER_LANE = 3,    // every lane (gene) has its own row in global memory (reference stream)
+};
+
 // Sequential member sum of one node for the 32 genes of a tile.
-//   SHARED_PERM: idx(m) = perm[cols[m]] is the same for all lanes: load 32 at a time, shuffle.
-//   otherwise  : each lane has its own permutation row `perm` (or none: identity).
-template <bool SHARED_PERM>
-__device__ __forceinline__ double node_sum(const double* __restrict__ ETt, const int32_t* __restrict__ cols,
-                                           const int32_t* __restrict__ perm, int beg, int end, int lane) {
+// Shared permutation: idx(m) = perm[cols[m]] is the same for all lanes: 32 composite indices are
+// loaded at a time (coalesced cols, then the gather through perm) and broadcast by shuffles with
+// immediate lane numbers.  `base` = tile pointer + lane, one opaque 64-bit value, so that every
+// gather address is a single IMAD.WIDE: the inner loop is SHFL + IMAD.WIDE + LDG.64 + DADD.
+template <int KIND>
+__device__ __forceinline__ double node_sum(const double* base, const int32_t* __restrict__ cols,
+                                           const int32_t* perm, int beg, int end, int lane) {
     double acc = 0.0;
-    const double* base = ETt + lane;
-    if (SHARED_PERM) {
+    if (KIND != PERM_PER_LANE) {
         for (int b = beg; b < end; b += 32) {
             int m = b + lane;
             int my = 0;
             if (m < end) {
                 my = __ldg(cols + m);
-                if (perm) my = __ldg(perm + my);
+                if (KIND == PERM_GLOBAL) my = __ldg(perm + my);
+                if (KIND == PERM_SMEM) my = perm[my];
             }
-            int cnt = min(32, end - b);
-            int t = 0;
-            for (; t + 8 <= cnt; t += 8) {
-                double v[8];
+            const int cnt = end - b;                 // > 0
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    int i = __shfl_sync(0xffffffffu, my, t + u);
-                    v[u] = __ldg(base + (size_t)i * kLanes);
+            for (int g8 = 0; g8 < 4; ++g8) {
+                if (cnt >= g8 * 8 + 8) {             // warp-uniform
+                    double v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        int i = __shfl_sync(0xffffffffu, my, g8 * 8 + u);
+                        v[u] = __ldg(base + (size_t)(unsigned)i * kLanes);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) acc += v[u];
                 }
-#pragma unroll
-                for (int u = 0; u < 8; ++u) acc += v[u];
             }
-            for (; t < cnt; ++t) {
-                int i = __shfl_sync(0xffffffffu, my, t);
-                acc += __ldg(base + (size_t)i * kLanes);
+            if (cnt < 32 && (cnt & 7)) {
+                for (int t = cnt & ~7; t < cnt; ++t) {
+                    int i = __shfl_sync(0xffffffffu, my, t);
+                    acc += __ldg(base + (size_t)(unsigned)i * kLanes);
+                }
             }
         }
     } else {
@@ -117,17 +142,41 @@ __device__ __forceinline__ double node_sum(const double* __restrict__ ETt, const
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 int i = __ldg(perm + __ldg(cols + m + u));
-                v[u] = __ldg(base + (size_t)i * kLanes);
+                v[u] = __ldg(base + (size_t)(unsigned)i * kLanes);
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) acc += v[u];
         }
         for (; m < end; ++m) {
             int i = __ldg(perm + __ldg(cols + m));
-            acc += __ldg(base + (size_t)i * kLanes);
+            acc += __ldg(base + (size_t)(unsigned)i * kLanes);
         }
     }
     return acc;
+}
+
+__device__ __forceinline__ void cp_async_4(void* smem_dst, const void* gmem_src) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_wait_all() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+
+// 1/q per node (ref:982-986 divide the member sum by the node size q).
+__global__ void inv_size_kernel(const int32_t* __restrict__ off, int V, double* __restrict__ inv_q) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < V) inv_q[k] = 1.0 / (double)(off[k + 1] - off[k]);
+}
+
+// float32(log1p(t1) / 0.693147) for t1 >= 0 (ref:983 and the float32 array of ref:972).
+__device__ __forceinline__ float pm_log2_value(double t1) {
+    const double c = 0.693147;
+    const double rc = 1.0 / 0.693147;                 // RN(1/c), folded at compile time
+    const bool zero = !(t1 > 0.0);
+    double l = log1p(zero ? 1.0 : t1);               // keep every lane on log1p's fast path
+    float r = (float)div_rn(l, c, rc);
+    return zero ? (float)t1 : r;                      // t1 == 0 -> 0; NaN propagates
 }
 
 struct PermArgs {
@@ -140,6 +189,7 @@ struct PermArgs {
     const int32_t* adj_idx;
     const double* adj_w;
     const double* ET;
+    const double* inv_q;
     const int32_t* perm;
     int64_t perm_gene_stride;
     const double* observed;
@@ -150,35 +200,65 @@ struct PermArgs {
     float* pm;                    // [gridDim.x][V][32]
 };
 
-template <int NW, bool SHARED_PERM>
+// STAGE: 0 = permutation rows read from global memory (KIND decides how), 1 = the current row is
+// copied to shared memory at the start of each permutation, 2 = double buffered: the next row is
+// prefetched by cp.async while the current one is processed (S*8 bytes of dynamic shared memory).
+template <int NW, int KIND, int STAGE>
 __global__ void __launch_bounds__(NW * 32) conn_perm_kernel(PermArgs a) {
     __shared__ double s_tot[NW][kLanes];
     __shared__ double s_part[NW][kLanes];
+    extern __shared__ int32_t s_perm[];              // [STAGE][S]
     const int lane = threadIdx.x & 31;
     const int w = threadIdx.x >> 5;
     float* pm = a.pm + (size_t)blockIdx.x * a.V * kLanes;
     const double cor = (double)a.V / (double)(a.V - 1);          // ref:989
+    int buf = 0;
+    if (STAGE == 2 && (int64_t)blockIdx.x < a.items) {            // prologue: first row of this CTA
+        const int r0 = (int)(blockIdx.x % a.nchunks) * kPermChunk;
+        const int32_t* src = a.perm + (size_t)r0 * a.S;
+        for (int i = threadIdx.x; i < a.S; i += NW * 32) cp_async_4(s_perm + i, src + i);
+    }
 
     for (int64_t item = blockIdx.x; item < a.items; item += gridDim.x) {
         const int tileIdx = (int)(item / a.nchunks);
         const int chunk = (int)(item % a.nchunks);
         const int g = tileIdx * kLanes + lane;
         const bool live = g < a.G;
-        const double* ETt = a.ET + (size_t)tileIdx * a.S * kLanes;
+        const double* base = a.ET + (size_t)tileIdx * a.S * kLanes + lane;
+        asm volatile("" : "+l"(base));               // opaque: gather address = base + idx*256 in one IMAD.WIDE
         const double obs = live ? a.observed[g] : 0.0;
         int cnt_exceed = 0, cnt_tie = 0;
         const int r_end = min(a.n, (chunk + 1) * kPermChunk);
         for (int r = chunk * kPermChunk; r < r_end; ++r) {
             const int32_t* perm_r;
-            if (SHARED_PERM) perm_r = a.perm + (size_t)r * a.S;
-            else perm_r = a.perm + (size_t)(live ? g : 0) * a.perm_gene_stride + (size_t)r * a.S;
+            if (KIND == PERM_PER_LANE) perm_r = a.perm + (size_t)(live ? g : 0) * a.perm_gene_stride + (size_t)r * a.S;
+            else perm_r = a.perm + (size_t)r * a.S;
+            if (STAGE == 1) {
+                for (int i = threadIdx.x; i < a.S; i += NW * 32) cp_async_4(s_perm + i, perm_r + i);
+                cp_async_commit_wait_all();
+                __syncthreads();
+                perm_r = s_perm;
+            }
+            if (STAGE == 2) {
+                cp_async_commit_wait_all();          // this thread's part of the current row has landed
+                __syncthreads();                     // ... and everybody else's
+                int rn = r + 1;                      // the row this CTA processes next, if any
+                if (rn >= r_end) rn = (item + gridDim.x < a.items) ? (int)((item + gridDim.x) % a.nchunks) * kPermChunk : -1;
+                if (rn >= 0) {
+                    const int32_t* src = a.perm + (size_t)rn * a.S;
+                    int32_t* dst = s_perm + (size_t)(buf ^ 1) * a.S;
+                    for (int i = threadIdx.x; i < a.S; i += NW * 32) cp_async_4(dst + i, src + i);
+                }
+                perm_r = s_perm + (size_t)buf * a.S;
+                buf ^= 1;
+            }
             // ---- node values (ref:978-987) ----
             double tot_w = 0.0;
             for (int k = w; k < a.V; k += NW) {
                 int beg = __ldg(a.node_off + k), end = __ldg(a.node_off + k + 1);
-                double acc = node_sum<SHARED_PERM>(ETt, a.node_cols, perm_r, beg, end, lane);
-                double t1 = acc / (double)(end - beg);
-                float pmv = a.log2_mode ? (float)(log1p(t1) / 0.693147) : (float)t1;   // ref:983/986, float32 store
+                double acc = node_sum<KIND>(base, a.node_cols, perm_r, beg, end, lane);
+                double t1 = div_rn(acc, (double)(end - beg), __ldg(a.inv_q + k));       // ref:982/986: sum / q
+                float pmv = a.log2_mode ? pm_log2_value(t1) : (float)t1;                // ref:983/986, float32 store
                 __stcg(pm + (size_t)k * kLanes + lane, pmv);
                 tot_w += (double)pmv;                                                   // ref:984
             }
@@ -260,12 +340,12 @@ __global__ void __launch_bounds__(NW * 32) node_stats_kernel(StatArgs a) {
     for (int tileIdx = blockIdx.x; tileIdx < a.tiles; tileIdx += gridDim.x) {
         const int g = tileIdx * kLanes + lane;
         const bool live = g < a.G;
-        const double* ETt = a.ET + (size_t)tileIdx * a.S * kLanes;
+        const double* base = a.ET + (size_t)tileIdx * a.S * kLanes + lane;
         // pol_k (ref:949-959)
         double tol_w = 0.0;
         for (int k = w; k < a.V; k += NW) {
             int beg = __ldg(a.node_off + k), end = __ldg(a.node_off + k + 1);
-            double acc = node_sum<true>(ETt, a.node_cols, nullptr, beg, end, lane);
+            double acc = node_sum<PERM_NONE>(base, a.node_cols, nullptr, beg, end, lane);
             double pol = acc / (double)(end - beg);
             if (a.log2_mode) pol = log2(1.0 + pol);
             __stcg(P + (size_t)k * kLanes + lane, pol);
@@ -326,6 +406,25 @@ __global__ void __launch_bounds__(NW * 32) node_stats_kernel(StatArgs a) {
         }
         __syncthreads();
     }
+}
+
+// div_rn against the IEEE division for pseudo-random numerators and the divisors the hot path
+// uses (node sizes 1..8192 and the constant 0.693147).
+__global__ void selftest_div_kernel(int64_t n, uint64_t seed, unsigned long long* mismatches) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t x = seed + 0x9E3779B97F4A7C15ull * (uint64_t)(i + 1);
+    x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 27; x *= 0x94D049BB133111EBull; x ^= x >> 31;
+    uint64_t mant = x & 0xFFFFFFFFFFFFFull;
+    int ex = (int)((x >> 52) & 63) - 24;                       // 2^-24 .. 2^39
+    double a = __longlong_as_double((long long)(((uint64_t)(1023 + ex) << 52) | mant));
+    if ((x >> 60) == 0) a = 0.0;
+    int q = (int)((x >> 40) % 8192) + 1;
+    double b = (double)q;
+    bool bad = __double_as_longlong(div_rn(a, b, 1.0 / b)) != __double_as_longlong(a / b);
+    const double c = 0.693147;
+    bad |= __double_as_longlong(div_rn(a, c, 1.0 / 0.693147)) != __double_as_longlong(a / c);
+    if (bad) atomicAdd(mismatches, 1ull);
 }
 
 int check_graph(sctda_ctx* ctx, const sctda_graph* gr) {
@@ -397,11 +496,11 @@ extern "C" int32_t sctda_conn_perm_test(sctda_ctx* ctx, const sctda_graph* gr, i
     if (rc) return rc;
     if (G < 0 || n < 0 || (G > 0 && !d_Y) || ldy < gr->Ncells)
         return sctda_fail(ctx, SCTDA_ERR_INVALID, "conn_perm_test: bad table (G/n < 0, NULL, or ldy < Ncells)%s");
+    if (G == 0) return SCTDA_OK;
     if (!d_exceed || !d_observed || (n > 0 && !d_perm))
         return sctda_fail(ctx, SCTDA_ERR_INVALID, "conn_perm_test: d_exceed, d_observed and d_perm are required%s");
     if (perm_gene_stride != 0 && perm_gene_stride < (int64_t)n * gr->S)
         return sctda_fail(ctx, SCTDA_ERR_INVALID, "conn_perm_test: perm_gene_stride must be 0 or >= n*S%s");
-    if (G == 0) return SCTDA_OK;
     cudaStream_t st = (cudaStream_t)stream;
     SCTDA_CUDA(ctx, cudaSetDevice(ctx->device));
     SCTDA_CUDA(ctx, cudaMemsetAsync(d_exceed, 0, (size_t)G * sizeof(int32_t), st));
@@ -410,7 +509,11 @@ extern "C" int32_t sctda_conn_perm_test(sctda_ctx* ctx, const sctda_graph* gr, i
     double* ET = nullptr;
     rc = launch_et_prep(ctx, gr, G, d_Y, ldy, log2_mode, &ET, st);
     if (rc) return rc;
-    constexpr int NW = 16;
+    double* inv_q = (double*)sctda_ws(ctx, WS_MISC, (size_t)gr->V * sizeof(double));
+    if (!inv_q) return SCTDA_ERR_NOMEM;
+    inv_size_kernel<<<(gr->V + 255) / 256, 256, 0, st>>>(gr->d_node_off, gr->V, inv_q);
+    SCTDA_LAUNCH_CHECK(ctx, "inv_size_kernel");
+    constexpr int NW = 32;
     PermArgs a;
     a.V = gr->V; a.S = gr->S; a.G = G; a.n = n; a.log2_mode = log2_mode;
     a.nchunks = (n + kPermChunk - 1) / kPermChunk;
@@ -418,18 +521,48 @@ extern "C" int32_t sctda_conn_perm_test(sctda_ctx* ctx, const sctda_graph* gr, i
     a.items = (int64_t)tiles * a.nchunks;
     a.node_off = gr->d_node_off; a.node_cols = gr->d_node_cols;
     a.adj_off = gr->d_adj_off; a.adj_idx = gr->d_adj_idx; a.adj_w = gr->d_adj_w;
-    a.ET = ET; a.perm = d_perm; a.perm_gene_stride = perm_gene_stride;
+    a.ET = ET; a.inv_q = inv_q; a.perm = d_perm; a.perm_gene_stride = perm_gene_stride;
     a.observed = d_observed; a.tie_rel = tie_rel > 0.0 ? tie_rel : 1e-9;
     a.exceed = d_exceed; a.ties = d_ties; a.scores = d_scores;
-    int64_t grid64 = (int64_t)ctx->sm_count * 2;
+    int64_t grid64 = (int64_t)ctx->sm_count;          // one 1024-thread CTA per SM: the node-value scratch stays in L2
     if (grid64 > a.items) grid64 = a.items;
     const int grid = (int)grid64;
     a.pm = (float*)sctda_ws(ctx, WS_PM, (size_t)grid * gr->V * kLanes * sizeof(float));
     if (!a.pm) return SCTDA_ERR_NOMEM;
+    // shared permutation rows are staged in shared memory when they fit (227 KB per CTA on sm_100a)
+    const size_t row_bytes = (size_t)gr->S * sizeof(int32_t);
+    const size_t smem_budget = 227 * 1024 - 2 * NW * kLanes * sizeof(double) - 1024;
     SCTDA_TIME_BEGIN(ctx, st);
-    if (perm_gene_stride == 0) conn_perm_kernel<NW, true><<<grid, NW * 32, 0, st>>>(a);
-    else conn_perm_kernel<NW, false><<<grid, NW * 32, 0, st>>>(a);
+    if (perm_gene_stride != 0) {
+        conn_perm_kernel<NW, PERM_PER_LANE, 0><<<grid, NW * 32, 0, st>>>(a);
+    } else if (2 * row_bytes <= smem_budget) {
+        auto kern = conn_perm_kernel<NW, PERM_SMEM, 2>;
+        SCTDA_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * row_bytes)));
+        kern<<<grid, NW * 32, 2 * row_bytes, st>>>(a);
+    } else if (row_bytes <= smem_budget) {
+        auto kern = conn_perm_kernel<NW, PERM_SMEM, 1>;
+        SCTDA_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_bytes));
+        kern<<<grid, NW * 32, row_bytes, st>>>(a);
+    } else {
+        conn_perm_kernel<NW, PERM_GLOBAL, 0><<<grid, NW * 32, 0, st>>>(a);
+    }
     SCTDA_TIME_END(ctx, st);
     SCTDA_LAUNCH_CHECK(ctx, "conn_perm_kernel");
+    return SCTDA_OK;
+}
+
+extern "C" int32_t sctda_selftest_div(sctda_ctx* ctx, int64_t n_trials, int64_t* out_mismatches) {
+    if (!ctx || !out_mismatches || n_trials < 0) return SCTDA_ERR_INVALID;
+    SCTDA_CUDA(ctx, cudaSetDevice(ctx->device));
+    unsigned long long* d = (unsigned long long*)sctda_ws(ctx, WS_MISC, 256);
+    if (!d) return SCTDA_ERR_NOMEM;
+    SCTDA_CUDA(ctx, cudaMemset(d, 0, sizeof(unsigned long long)));
+    if (n_trials > 0) {
+        selftest_div_kernel<<<(unsigned)cdiv64(n_trials, 256), 256>>>(n_trials, 0x5c7da5eedull, d);
+        SCTDA_LAUNCH_CHECK(ctx, "selftest_div_kernel");
+    }
+    unsigned long long h = 0;
+    SCTDA_CUDA(ctx, cudaMemcpy(&h, d, sizeof(h), cudaMemcpyDeviceToHost));
+    *out_mismatches = (int64_t)h;
     return SCTDA_OK;
 }

@@ -73,6 +73,11 @@ class DeviceGraph(object):
         if off[-1] >= 2 ** 31 or samples.size >= 2 ** 31:
             raise ValueError('graph too large for int32 indices')
         adj_csr = scipy.sparse.csr_matrix(adj_csr, dtype=numpy.float64)
+        # the library only evaluates the quadratic form p'Ap (include/sctda_b200.h): hand it the
+        # upper-triangular matrix with the same form, half the non-zeros of the symmetric adjacency
+        adj_csr = scipy.sparse.csr_matrix(scipy.sparse.triu(adj_csr + adj_csr.T, k=1)
+                                          + scipy.sparse.diags(adj_csr.diagonal()))
+        adj_csr.sort_indices()
         self.V, self.S, self.Ncells = V, int(samples.size), int(n_cells)
         self.Mtot = int(off[-1])
         self.nnz = int(adj_csr.nnz)
