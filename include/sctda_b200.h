@@ -153,6 +153,74 @@ int32_t sctda_conn_perm_test(sctda_ctx* ctx, const sctda_graph* graph,
                              int32_t* d_exceed, int32_t* d_ties, double* d_scores,
                              void* stream);
 
+/* ---- hot path (a): Mapper graph build ------------------------------------------------------- */
+/*
+ * The reference reaches this path through the third-party package sakmapper:
+ *   sakmapper.apply_lens(df, lens='mds', metric=...)           /root/reference/scTDA/main.py:746-751
+ *   sakmapper.mapper_graph(df, lens_data, resolution, gain, equalize, clust, stat, max_K)   :768-771
+ * The entry points below are the stages of mapper_graph (cover -> per-patch clustering -> nodes
+ * -> nerve) and the distance contraction behind apply_lens(lens='mds').  The algorithm and every
+ * choice the call sites leave open are stated in oracle/mapper_oracle.py.
+ * Variable-size outputs use a count call (sizes to the device, read by the caller) then a fill
+ * call; the context keeps the intermediate state between the two.
+ */
+
+/* Xn = X (mode 0, metric 'euclidean') or the centred, unit-norm rows of X (mode 1, 'correlation';
+ * constant rows become zeros); d_sq[i] = |Xn_i|^2 (may be NULL).  Columns G..ldxn-1 of Xn are
+ * zeroed.  Sums run in a fixed order (lane-strided partials, xor butterfly). */
+int32_t sctda_row_normalize_f64(sctda_ctx* ctx, int32_t N, int32_t G, const double* d_X, int64_t ldx,
+                                int32_t mode, double* d_Xn, int64_t ldxn, double* d_sq, void* stream);
+
+/* out[i][j] = sum_k Xn[rows_a[i]][k] * Xn[rows_b[j]][k]  (FP64 tensor-pipe MMA, one fused
+ * multiply-add chain over k ascending per element).  rows_* may be NULL (identity).
+ * Rows must be 16-byte aligned: ldxn even. */
+int32_t sctda_gram_gather_f64(sctda_ctx* ctx, int32_t G, const double* d_Xn, int64_t ldxn,
+                              int32_t na, const int32_t* d_rows_a, int32_t nb, const int32_t* d_rows_b,
+                              double* d_out, int64_t ldo, void* stream);
+
+/* Rows [r0, r1) of the N x N dissimilarity that apply_lens(lens='mds', metric=...) hands to MDS:
+ * metric 0 = euclidean  sqrt(max(0, (sq_i + sq_j) - 2 G_ij)),  metric 1 = correlation 1 - G_ij on
+ * the mode-1 rows; the diagonal is exactly 0.  d_D is [r1-r0, ldd]. */
+int32_t sctda_pairdist_rows_f64(sctda_ctx* ctx, int32_t N, int32_t G, const double* d_Xn, int64_t ldxn,
+                                const double* d_sq, int32_t r0, int32_t r1, int32_t metric,
+                                double* d_D, int64_t ldd, void* stream);
+
+/* Cover (mapper_graph stage 1).  d_lens [N, ldl>=2]: the 2-D lens.  d_lo0, d_hi0, d_lo1, d_hi1 [r]: open interval
+ * bounds per axis (fenceposts widened by gain; the host computes them from percentiles).
+ * Patch b = i*r + j holds the cells with lo0[i] < lens0 < hi0[i] and lo1[j] < lens1 < hi1[j].
+ * count: d_bin_off [r*r + 1] exclusive offsets (last = total memberships).  fill: d_members
+ * [total], ascending cell index inside each patch.  r <= 128. */
+int32_t sctda_cover_count(sctda_ctx* ctx, int32_t N, const double* d_lens, int64_t ldl, int32_t r,
+                          const double* d_lo0, const double* d_hi0, const double* d_lo1,
+                          const double* d_hi1, int32_t* d_bin_off, void* stream);
+int32_t sctda_cover_fill(sctda_ctx* ctx, int32_t N, int32_t r, const int32_t* d_bin_off,
+                         int32_t* d_members, void* stream);
+
+/* Per-patch clustering (mapper_graph stage 2): single linkage (MST) on squared Euclidean
+ * distances between the rows of Xn, K in 2..K_max chosen by the Davies-Bouldin index
+ * (stat 0 = 'db'), K_max = 2 if m <= 5 else min(m/2, max_K); a one-cell patch is one node.
+ * d_labels [total] cluster of each membership (numbered by smallest member), d_bin_K [nbins],
+ * d_bin_db [nbins, 8] the index of K = 2, 3, ... (NaN where not evaluated; may be NULL).
+ * Synchronises the host once (workspace sizing).  max_K <= 8, patches of <= 10,000 cells. */
+int32_t sctda_bin_cluster(sctda_ctx* ctx, int32_t G, const double* d_Xn, int64_t ldxn, int32_t nbins,
+                          const int32_t* d_bin_off, const int32_t* d_members, int32_t max_K, int32_t stat,
+                          int32_t* d_labels, int32_t* d_bin_K, double* d_bin_db, void* stream);
+
+/* Node lists (all_clusters of ref:772-774): nodes ordered by (patch, cluster).  count:
+ * d_node_base [nbins+1] (last = V).  fill: d_node_off [V+1], d_node_members [total] ascending,
+ * d_node_bin [V]. */
+int32_t sctda_nodes_count(sctda_ctx* ctx, int32_t nbins, const int32_t* d_bin_K, int32_t* d_node_base,
+                          void* stream);
+int32_t sctda_nodes_fill(sctda_ctx* ctx, int32_t nbins, const int32_t* d_bin_off, const int32_t* d_members,
+                         const int32_t* d_labels, const int32_t* d_node_base, int32_t V,
+                         int32_t* d_node_off, int32_t* d_node_members, int32_t* d_node_bin, void* stream);
+
+/* Nerve (mapper_graph stage 3): edge (i < j) iff nodes i and j share a cell.  count: *d_edge_count
+ * (int64 on the device).  fill: d_edges [E, 2] int32, sorted lexicographically.  V <= 131,072. */
+int32_t sctda_nerve_count(sctda_ctx* ctx, int32_t N, int32_t V, const int32_t* d_node_off,
+                          const int32_t* d_node_members, int64_t Mtot, int64_t* d_edge_count, void* stream);
+int32_t sctda_nerve_fill(sctda_ctx* ctx, int32_t V, int32_t* d_edges, void* stream);
+
 /*
  * Diagnostic: the permutation kernel divides with a reciprocal and one fused correction step
  * instead of the generic IEEE division; this runs n_trials pseudo-random comparisons of the

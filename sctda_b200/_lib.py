@@ -42,6 +42,18 @@ SIGNATURES = {
     'sctda_launch_count': (c_i64, [c_ptr]),
     'sctda_set_kernel_timing': (c_i32, [c_ptr, c_i32]),
     'sctda_last_kernel_ms': (c_i32, [c_ptr, ctypes.POINTER(ctypes.c_float)]),
+    'sctda_row_normalize_f64': (c_i32, [c_ptr, c_i32, c_i32, c_ptr, c_i64, c_i32, c_ptr, c_i64, c_ptr, c_ptr]),
+    'sctda_gram_gather_f64': (c_i32, [c_ptr, c_i32, c_ptr, c_i64, c_i32, c_ptr, c_i32, c_ptr, c_ptr, c_i64, c_ptr]),
+    'sctda_pairdist_rows_f64': (c_i32, [c_ptr, c_i32, c_i32, c_ptr, c_i64, c_ptr, c_i32, c_i32, c_i32, c_ptr, c_i64,
+                                        c_ptr]),
+    'sctda_cover_count': (c_i32, [c_ptr, c_i32, c_ptr, c_i64, c_i32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
+    'sctda_cover_fill': (c_i32, [c_ptr, c_i32, c_i32, c_ptr, c_ptr, c_ptr]),
+    'sctda_bin_cluster': (c_i32, [c_ptr, c_i32, c_ptr, c_i64, c_i32, c_ptr, c_ptr, c_i32, c_i32, c_ptr, c_ptr, c_ptr,
+                                  c_ptr]),
+    'sctda_nodes_count': (c_i32, [c_ptr, c_i32, c_ptr, c_ptr, c_ptr]),
+    'sctda_nodes_fill': (c_i32, [c_ptr, c_i32, c_ptr, c_ptr, c_ptr, c_ptr, c_i32, c_ptr, c_ptr, c_ptr, c_ptr]),
+    'sctda_nerve_count': (c_i32, [c_ptr, c_i32, c_i32, c_ptr, c_ptr, c_i64, c_ptr, c_ptr]),
+    'sctda_nerve_fill': (c_i32, [c_ptr, c_i32, c_ptr, c_ptr]),
     'sctda_selftest_div': (c_i32, [c_ptr, c_i64, ctypes.POINTER(c_i64)]),
     'sctda_node_stats': (c_i32, [c_ptr, ctypes.POINTER(Graph), c_i32, c_ptr, c_i64, c_i32, c_ptr,
                                  c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),

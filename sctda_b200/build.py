@@ -16,6 +16,11 @@ NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', 
               '-Xcompiler', '-fPIC', '-I', os.path.join(ROOT, 'include')]
 
 
+# sources whose float64 arithmetic must not be contracted into FMAs by the compiler (explicit
+# __fma_rn only): their results are compared bit for bit with the scalar oracle
+NO_FMAD = ('cluster.cu', 'dist.cu')
+
+
 def _nvcc():
     for c in (os.environ.get('NVCC'), '/usr/local/cuda/bin/nvcc', 'nvcc'):
         if c and (os.path.isabs(c) and os.path.exists(c) or not os.path.isabs(c)):
@@ -45,7 +50,8 @@ def build(force=False, verbose=False):
         obj = src[:-3] + '.o'
         objs.append(obj)
         if force or _stale(obj, [src] + headers):
-            cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-c', src, '-o', obj]
+            extra = ['-fmad=false'] if os.path.basename(src) in NO_FMAD else []   # fixed operation order
+            cmd = [nvcc] + NVCC_FLAGS + extra + (['-Xptxas', '-v'] if verbose else []) + ['-c', src, '-o', obj]
             procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
     for cmd, p in procs:
         out = p.communicate()[0].decode()

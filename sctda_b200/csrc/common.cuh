@@ -33,6 +33,7 @@ enum {
     WS_NERVE = 6,
     WS_CLUSTER2 = 7,
     WS_CLUSTER3 = 8,
+    WS_NODES = 9,
 };
 
 static inline int sctda_fail(sctda_ctx* ctx, int code, const char* fmt, const char* a = "", long long b = 0) {

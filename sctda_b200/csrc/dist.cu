@@ -1,0 +1,310 @@
+// Hot path (a), stage 1: row normalisation and the cells x cells Gram / distance contraction.
+//
+// Reference seam: sakmapper.apply_lens(..., metric=...) builds the N x N dissimilarity for the MDS
+// lens (/root/reference/scTDA/main.py:746-751) and sakmapper.mapper_graph clusters every cover
+// patch on distances between its rows (:768-771).  Both reduce to
+//     G[i][j] = sum_k Xn[ra[i]][k] * Xn[rb[j]][k]
+// over row index lists (a row block against all rows, or a patch against itself).
+//
+// Design (sm_100a).  tcgen05 has no FP64 kind, so the one dense contraction of the path runs
+// on the FP64 tensor pipe through warp-level mma.sync.m8n8k4 (DMMA): 128x128 CTA tile, 8 warps
+// of 32x64, K staged 16 columns at a time through a 3-stage cp.async ring.  Rows are GATHERED
+// (index lists), which a tiled TMA box cannot express, so the staging is 16-byte cp.async with
+// zero-fill on the K tail; shared-memory rows are padded to 20 doubles so that the 8x4 fragment
+// loads of each half warp hit 32 distinct banks.  K is walked sequentially with no split-K:
+// every output element is ONE chain of fused multiply-adds over k ascending, which makes the
+// result reproducible bit for bit by a scalar fma loop (oracle/mapper_oracle.c).
+#include <math.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 16, LDS = 20, STAGES = 3;
+constexpr int GEMM_THREADS = 256;
+constexpr int STAGE_DOUBLES = (BM + BN) * LDS;
+constexpr size_t GEMM_SMEM = (size_t)STAGES * STAGE_DOUBLES * sizeof(double);
+
+enum { EPI_GRAM = 0, EPI_EUCLID = 1, EPI_CORR = 2 };
+
+__device__ __forceinline__ void cp_async_16_zfill(void* smem_dst, const void* gmem_src, int src_bytes) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gmem_src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void dmma_884(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+// One batched problem: out[i][j] for i < na, j < nb.
+struct GemmProblem {
+    const int32_t* rows_a;   // row indices into X (NULL: identity + row0_a)
+    const int32_t* rows_b;
+    int row0_a, row0_b;
+    int na, nb;
+    double* out;
+    int64_t ldo;
+};
+
+struct GemmArgs {
+    const double* X;         // [*, ldx]
+    int64_t ldx;
+    int G;                   // features (K of the GEMM)
+    const double* sq;        // |row|^2 (EUCLID epilogue)
+    int epilogue;
+    // single problem (nprob == 0) or batched patches
+    GemmProblem single;
+    int nprob;
+    const int32_t* bin_off;      // [nprob+1] member offsets
+    const int32_t* members;      // [Mtot]
+    const int64_t* tile_prefix;  // [nprob+1] number of 128x128 tiles before problem p
+    const int64_t* gram_off;     // [nprob+1] element offset of problem p's m x m output
+    double* gram;
+};
+
+__device__ __forceinline__ void gemm_tile(const GemmArgs& a, const GemmProblem& pr, int ti, int tj, double* smem) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp & 3, wn = warp >> 2;                 // 4 x 2 warps, warp tile 32 x 64
+    const int m0 = ti * BM, n0 = tj * BN;
+    // this thread's cp.async assignments: chunk c = tid + 256*i  ->  row c/8, 16-byte column c%8
+    const double* srcA[4];
+    const double* srcB[4];
+    int dst_off[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int c = tid + GEMM_THREADS * i;
+        int r = c >> 3, q = c & 7;
+        int ra = min(m0 + r, pr.na - 1), rb = min(n0 + r, pr.nb - 1);
+        int64_t ga = pr.rows_a ? (int64_t)pr.rows_a[ra] : (int64_t)(pr.row0_a + ra);
+        int64_t gb = pr.rows_b ? (int64_t)pr.rows_b[rb] : (int64_t)(pr.row0_b + rb);
+        srcA[i] = a.X + ga * a.ldx + q * 2;
+        srcB[i] = a.X + gb * a.ldx + q * 2;
+        dst_off[i] = r * LDS + q * 2;
+    }
+    const int ksteps = (a.G + BK - 1) / BK;
+    auto issue = [&](int ks) {
+        double* sA = smem + (size_t)(ks % STAGES) * STAGE_DOUBLES;
+        double* sB = sA + BM * LDS;
+        const int k0 = ks * BK;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            int q2 = (dst_off[i] % LDS);                      // column (doubles) of this chunk
+            int remain = a.G - (k0 + q2);                     // doubles left in the row from here
+            int bytes = remain >= 2 ? 16 : (remain == 1 ? 8 : 0);
+            cp_async_16_zfill(sA + dst_off[i], bytes ? (const void*)(srcA[i] + k0) : (const void*)a.X, bytes);
+            cp_async_16_zfill(sB + dst_off[i], bytes ? (const void*)(srcB[i] + k0) : (const void*)a.X, bytes);
+        }
+    };
+    double acc[4][8][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) {
+        if (s < ksteps) issue(s);
+        cp_async_commit();
+    }
+    const int fr = lane >> 2, fc = lane & 3;
+    for (int ks = 0; ks < ksteps; ++ks) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        if (ks + STAGES - 1 < ksteps) issue(ks + STAGES - 1);
+        cp_async_commit();
+        const double* sA = smem + (size_t)(ks % STAGES) * STAGE_DOUBLES + (wm * 32 + fr) * LDS + fc;
+        const double* sB = smem + (size_t)(ks % STAGES) * STAGE_DOUBLES + BM * LDS + (wn * 64 + fr) * LDS + fc;
+#pragma unroll
+        for (int kk = 0; kk < BK / 4; ++kk) {
+            double fa[4], fb[8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) fa[i] = sA[i * 8 * LDS + kk * 4];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) fb[j] = sB[j * 8 * LDS + kk * 4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) dmma_884(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
+        }
+    }
+    cp_async_wait<0>();
+    __syncthreads();                                          // smem is reused by the next tile
+    // epilogue: thread holds rows fr (+8*i), columns 2*fc, 2*fc+1 (+8*j) of its warp tile
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = m0 + wm * 32 + i * 8 + fr;
+        if (r >= pr.na) continue;
+        const int64_t gr = pr.rows_a ? (int64_t)pr.rows_a[r] : (int64_t)(pr.row0_a + r);
+        const double sqr = (a.epilogue == EPI_EUCLID) ? a.sq[gr] : 0.0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int c = n0 + wn * 64 + j * 8 + fc * 2 + e;
+                if (c >= pr.nb) continue;
+                double v = acc[i][j][e];
+                if (a.epilogue != EPI_GRAM) {
+                    const int64_t gc = pr.rows_b ? (int64_t)pr.rows_b[c] : (int64_t)(pr.row0_b + c);
+                    if (a.epilogue == EPI_EUCLID) v = sqrt(fmax(fma(-2.0, v, __dadd_rn(sqr, a.sq[gc])), 0.0));
+                    else v = __dsub_rn(1.0, v);
+                    if (gr == gc) v = 0.0;
+                }
+                pr.out[(int64_t)r * pr.ldo + c] = v;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(GemmArgs a) {
+    extern __shared__ __align__(16) double smem[];
+    if (a.nprob == 0) {
+        const int tn = (a.single.nb + BN - 1) / BN;
+        const int64_t total = (int64_t)((a.single.na + BM - 1) / BM) * tn;
+        for (int64_t t = blockIdx.x; t < total; t += gridDim.x) gemm_tile(a, a.single, (int)(t / tn), (int)(t % tn), smem);
+        return;
+    }
+    const int64_t total = a.tile_prefix[a.nprob];
+    for (int64_t t = blockIdx.x; t < total; t += gridDim.x) {
+        int lo = 0, hi = a.nprob;                             // last p with tile_prefix[p] <= t
+        while (hi - lo > 1) {
+            int mid = (lo + hi) >> 1;
+            if (a.tile_prefix[mid] <= t) lo = mid; else hi = mid;
+        }
+        const int m = a.bin_off[lo + 1] - a.bin_off[lo];
+        const int tn = (m + BN - 1) / BN;
+        const int64_t lt = t - a.tile_prefix[lo];
+        GemmProblem pr;
+        pr.rows_a = pr.rows_b = a.members + a.bin_off[lo];
+        pr.row0_a = pr.row0_b = 0;
+        pr.na = pr.nb = m;
+        pr.out = a.gram + a.gram_off[lo];
+        pr.ldo = m;
+        gemm_tile(a, pr, (int)(lt / tn), (int)(lt % tn), smem);
+    }
+}
+
+// Row statistics in a fixed order: lane l adds elements l, l+32, ... sequentially, then the
+// xor butterfly 16, 8, 4, 2, 1 (oracle/mapper_oracle.py:_lane_sums).  One warp per row.
+__device__ __forceinline__ double warp_tree(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+__global__ void __launch_bounds__(256) row_normalize_kernel(const double* __restrict__ X, int64_t ldx, int N, int G,
+                                                            int mode, double* __restrict__ Xn, int64_t ldxn,
+                                                            double* __restrict__ sq) {
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= N) return;
+    const double* x = X + (int64_t)row * ldx;
+    double* y = Xn + (int64_t)row * ldxn;
+    double mean = 0.0, inv_valid = 0.0, nrm = 1.0;
+    if (mode == 1) {
+        double s = 0.0;
+        for (int k = lane; k < G; k += 32) s = __dadd_rn(s, x[k]);
+        mean = __ddiv_rn(warp_tree(s), (double)G);
+        double ss = 0.0;
+        for (int k = lane; k < G; k += 32) {
+            double c = __dsub_rn(x[k], mean);
+            ss = __dadd_rn(ss, __dmul_rn(c, c));
+        }
+        nrm = sqrt(warp_tree(ss));
+        inv_valid = nrm > 0.0 ? 1.0 : 0.0;
+    }
+    double s2 = 0.0;
+    for (int k = lane; k < G; k += 32) {
+        double v = x[k];
+        if (mode == 1) v = inv_valid != 0.0 ? __ddiv_rn(__dsub_rn(v, mean), nrm) : 0.0;
+        y[k] = v;
+        s2 = __dadd_rn(s2, __dmul_rn(v, v));
+    }
+    for (int k = G + lane; k < ldxn; k += 32) y[k] = 0.0;    // zero the padding of the leading dimension
+    s2 = warp_tree(s2);
+    if (lane == 0 && sq) sq[row] = s2;
+}
+
+int launch_gemm(sctda_ctx* ctx, const GemmArgs& a, int64_t tiles_hint, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        SCTDA_CUDA(ctx, cudaFuncSetAttribute(gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
+        attr_set = true;
+    }
+    int64_t grid = tiles_hint > 0 ? tiles_hint : ctx->sm_count;
+    if (grid > ctx->sm_count) grid = ctx->sm_count;          // persistent: one CTA per SM
+    if (grid < 1) grid = 1;
+    SCTDA_TIME_BEGIN(ctx, st);
+    gemm_kernel<<<(unsigned)grid, GEMM_THREADS, GEMM_SMEM, st>>>(a);
+    SCTDA_TIME_END(ctx, st);
+    SCTDA_LAUNCH_CHECK(ctx, "gemm_kernel");
+    return SCTDA_OK;
+}
+
+}  // namespace
+
+// Batched patch Gram matrices for the clustering stage (cluster.cu).
+int sctda_internal_gram_bins(sctda_ctx* ctx, int G, const double* d_Xn, int64_t ldxn, int nbins,
+                             const int32_t* d_bin_off, const int32_t* d_members, const int64_t* d_tile_prefix,
+                             const int64_t* d_gram_off, double* d_gram, cudaStream_t st) {
+    GemmArgs a;
+    memset(&a, 0, sizeof(a));
+    a.X = d_Xn; a.ldx = ldxn; a.G = G; a.epilogue = EPI_GRAM;
+    a.nprob = nbins; a.bin_off = d_bin_off; a.members = d_members;
+    a.tile_prefix = d_tile_prefix; a.gram_off = d_gram_off; a.gram = d_gram;
+    return launch_gemm(ctx, a, 0, st);
+}
+
+extern "C" int32_t sctda_row_normalize_f64(sctda_ctx* ctx, int32_t N, int32_t G, const double* d_X, int64_t ldx,
+                                           int32_t mode, double* d_Xn, int64_t ldxn, double* d_sq, void* stream) {
+    if (!ctx) return SCTDA_ERR_INVALID;
+    if (N < 0 || G < 1 || !d_X || !d_Xn || ldx < G || ldxn < G || (mode != 0 && mode != 1))
+        return sctda_fail(ctx, SCTDA_ERR_INVALID, "row_normalize: bad arguments%s");
+    if (N == 0) return SCTDA_OK;
+    SCTDA_CUDA(ctx, cudaSetDevice(ctx->device));
+    row_normalize_kernel<<<(unsigned)cdiv64((int64_t)N * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+        d_X, ldx, N, G, mode, d_Xn, ldxn, d_sq);
+    SCTDA_LAUNCH_CHECK(ctx, "row_normalize_kernel");
+    return SCTDA_OK;
+}
+
+extern "C" int32_t sctda_gram_gather_f64(sctda_ctx* ctx, int32_t G, const double* d_Xn, int64_t ldxn, int32_t na,
+                                         const int32_t* d_rows_a, int32_t nb, const int32_t* d_rows_b, double* d_out,
+                                         int64_t ldo, void* stream) {
+    if (!ctx) return SCTDA_ERR_INVALID;
+    if (G < 1 || na < 0 || nb < 0 || !d_Xn || !d_out || ldxn < G || ldo < nb)
+        return sctda_fail(ctx, SCTDA_ERR_INVALID, "gram_gather: bad arguments%s");
+    if ((ldxn & 1) || ((uintptr_t)d_Xn & 15))
+        return sctda_fail(ctx, SCTDA_ERR_UNSUPPORTED, "gram_gather: rows must be 16-byte aligned (even ldxn)%s");
+    if (na == 0 || nb == 0) return SCTDA_OK;
+    SCTDA_CUDA(ctx, cudaSetDevice(ctx->device));
+    GemmArgs a;
+    memset(&a, 0, sizeof(a));
+    a.X = d_Xn; a.ldx = ldxn; a.G = G; a.epilogue = EPI_GRAM;
+    a.single.rows_a = d_rows_a; a.single.rows_b = d_rows_b; a.single.na = na; a.single.nb = nb;
+    a.single.out = d_out; a.single.ldo = ldo;
+    return launch_gemm(ctx, a, cdiv64(na, BM) * cdiv64(nb, BN), (cudaStream_t)stream);
+}
+
+extern "C" int32_t sctda_pairdist_rows_f64(sctda_ctx* ctx, int32_t N, int32_t G, const double* d_Xn, int64_t ldxn,
+                                           const double* d_sq, int32_t r0, int32_t r1, int32_t metric, double* d_D,
+                                           int64_t ldd, void* stream) {
+    if (!ctx) return SCTDA_ERR_INVALID;
+    if (N < 1 || G < 1 || !d_Xn || !d_D || r0 < 0 || r1 < r0 || r1 > N || ldxn < G || ldd < N ||
+        (metric != 0 && metric != 1) || (metric == 0 && !d_sq))
+        return sctda_fail(ctx, SCTDA_ERR_INVALID, "pairdist_rows: bad arguments%s");
+    if ((ldxn & 1) || ((uintptr_t)d_Xn & 15))
+        return sctda_fail(ctx, SCTDA_ERR_UNSUPPORTED, "pairdist_rows: rows must be 16-byte aligned (even ldxn)%s");
+    if (r1 == r0) return SCTDA_OK;
+    SCTDA_CUDA(ctx, cudaSetDevice(ctx->device));
+    GemmArgs a;
+    memset(&a, 0, sizeof(a));
+    a.X = d_Xn; a.ldx = ldxn; a.G = G; a.sq = d_sq;
+    a.epilogue = metric == 0 ? EPI_EUCLID : EPI_CORR;
+    a.single.row0_a = r0; a.single.na = r1 - r0; a.single.row0_b = 0; a.single.nb = N;
+    a.single.out = d_D; a.single.ldo = ldd;
+    return launch_gemm(ctx, a, cdiv64(r1 - r0, BM) * cdiv64(N, BN), (cudaStream_t)stream);
+}

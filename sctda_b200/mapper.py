@@ -1,0 +1,289 @@
+"""Host-side mirror of the Mapper seam of scTDA: sakmapper.apply_lens / sakmapper.mapper_graph as
+scTDA calls them (/root/reference/scTDA/main.py:744-753, 768-771, "ref:") and
+scTDA.TopologicalRepresentation (ref:731-778), with the cover, the per-patch clustering, the node
+lists and the nerve computed by the CUDA kernels behind include/sctda_b200.h.
+
+The Mapper algorithm itself is not in the reference tree (sakmapper is an absent third-party
+dependency); what is built here is the algorithm restated in oracle/mapper_oracle.py, with the
+call-site contract of the reference: mapper_graph returns (G, all_clusters, patches), G's nodes
+0..V-1 enumerate all_clusters, TopologicalRepresentation.save writes name.json + name.gexf.
+There is no CPU fallback for the graph build.
+"""
+import ctypes
+
+import numpy
+import torch
+
+from . import _lib
+from . import formats
+
+
+def _stream(dev):
+    return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _padded_device_table(X, dev):
+    """float64 device copy of a cells x genes table with an even leading dimension (the
+    contraction kernel stages 16-byte chunks)."""
+    if isinstance(X, torch.Tensor):
+        Xd = X.to(dev, dtype=torch.float64)
+    else:
+        Xd = torch.from_numpy(numpy.ascontiguousarray(numpy.asarray(X, dtype=numpy.float64))).to(dev)
+    n, g = Xd.shape
+    if g % 2 == 0 and Xd.stride(1) == 1 and Xd.stride(0) % 2 == 0 and Xd.data_ptr() % 16 == 0:
+        return Xd
+    out = torch.zeros((n, g + (g % 2)), dtype=torch.float64, device=dev)
+    out[:, :g] = Xd
+    return out[:, :g]
+
+
+def row_normalize(ctx, Xd, metric):
+    """sctda_row_normalize_f64: (Xn [N, G] view of an even-ld buffer, sq [N])."""
+    dev = Xd.device
+    n, g = Xd.shape
+    ld = g + (g % 2)
+    buf = torch.empty((n, ld), dtype=torch.float64, device=dev)
+    sq = torch.empty(n, dtype=torch.float64, device=dev)
+    mode = {'euclidean': 0, 'correlation': 1}[metric]
+    ctx.check(ctx.lib.sctda_row_normalize_f64(ctx.handle, n, g, _lib.ptr(Xd), int(Xd.stride(0)), mode, _lib.ptr(buf), ld,
+                                              _lib.ptr(sq), _stream(dev)))
+    return buf[:, :g], sq
+
+
+def pairwise_distances(ctx, Xd, metric, row_block=8192):
+    """The N x N dissimilarity of apply_lens(lens='mds', metric=...) (ref:746-751), computed
+    row block by row block on the device."""
+    dev = Xd.device
+    Xn, sq = row_normalize(ctx, Xd, metric)
+    n, g = Xn.shape
+    D = torch.empty((n, n), dtype=torch.float64, device=dev)
+    code = {'euclidean': 0, 'correlation': 1}[metric]
+    for r0 in range(0, n, row_block):
+        r1 = min(n, r0 + row_block)
+        ctx.check(ctx.lib.sctda_pairdist_rows_f64(ctx.handle, n, g, _lib.ptr(Xn), int(Xn.stride(0)), _lib.ptr(sq), r0, r1,
+                                                  code, _lib.ptr(D[r0:r1]), n, _stream(dev)))
+    return D
+
+
+def gram_gather(ctx, Xn, rows_a, rows_b):
+    dev = Xn.device
+    ra = torch.as_tensor(rows_a, dtype=torch.int32, device=dev).contiguous()
+    rb = torch.as_tensor(rows_b, dtype=torch.int32, device=dev).contiguous()
+    out = torch.empty((ra.numel(), rb.numel()), dtype=torch.float64, device=dev)
+    ctx.check(ctx.lib.sctda_gram_gather_f64(ctx.handle, int(Xn.shape[1]), _lib.ptr(Xn), int(Xn.stride(0)), ra.numel(),
+                                            _lib.ptr(ra), rb.numel(), _lib.ptr(rb), _lib.ptr(out), rb.numel(), _stream(dev)))
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# cover bounds (host: 2(r+1) order statistics of the lens)
+# ----------------------------------------------------------------------------------------------
+def cover_bounds(lens, resolution, gain, equalize=True):
+    """Open interval bounds per axis: fenceposts = numpy.percentile(axis, k*100/r) (equalize) or
+    evenly spaced between min and max, each interval widened by gain/2 of its width on both sides
+    (SURVEY.md appendix C.2)."""
+    lens = numpy.asarray(lens, dtype=numpy.float64)
+    r = int(resolution)
+    out = []
+    for ax in (0, 1):
+        v = lens[:, ax]
+        if equalize:
+            posts = numpy.array([numpy.percentile(v, k * 100.0 / r) for k in range(r + 1)])
+        else:
+            posts = numpy.linspace(v.min(), v.max(), r + 1)
+        w = posts[1:] - posts[:-1]
+        out += [posts[:-1] - (0.5 * gain) * w, posts[1:] + (0.5 * gain) * w]
+    return out
+
+
+class MapperDeviceResult(object):
+    """Device-resident result of one graph build (all int32 tensors)."""
+    __slots__ = ('r', 'bin_off', 'members', 'labels', 'bin_K', 'bin_db', 'V', 'node_off', 'node_members', 'node_bin',
+                 'E', 'edges')
+
+
+def build_graph_device(ctx, Xd, lens, resolution, gain, equalize=True, stat='db', max_K=5, metric='euclidean',
+                       bounds=None):
+    """normalise -> cover -> per-patch clustering -> nodes -> nerve, everything on the device.
+    Xd: [N, G] float64 device tensor (even leading dimension); lens: [N, 2] host or device."""
+    dev = Xd.device
+    N, G = Xd.shape
+    r = int(resolution)
+    if stat != 'db':
+        raise NotImplementedError("statistics=%r: only 'db' is served by the device path" % (stat,))
+    if not isinstance(lens, torch.Tensor):
+        lens = numpy.array(lens, dtype=numpy.float64)
+    lens_d = torch.as_tensor(lens, dtype=torch.float64).to(dev).contiguous()
+    if bounds is None:
+        bounds = cover_bounds(lens_d.cpu().numpy(), r, gain, equalize)
+    b = [torch.from_numpy(numpy.ascontiguousarray(x)).to(dev) for x in bounds]
+    st = _stream(dev)
+    Xn, _ = row_normalize(ctx, Xd, metric)
+    res = MapperDeviceResult()
+    res.r = r
+    B = r * r
+    res.bin_off = torch.empty(B + 1, dtype=torch.int32, device=dev)
+    ctx.check(ctx.lib.sctda_cover_count(ctx.handle, N, _lib.ptr(lens_d), 2, r, _lib.ptr(b[0]), _lib.ptr(b[1]),
+                                        _lib.ptr(b[2]), _lib.ptr(b[3]), _lib.ptr(res.bin_off), st))
+    mtot = int(res.bin_off[B].item())
+    res.members = torch.empty(max(mtot, 1), dtype=torch.int32, device=dev)[:mtot]
+    ctx.check(ctx.lib.sctda_cover_fill(ctx.handle, N, r, _lib.ptr(res.bin_off), ctypes.c_void_p(res.members.data_ptr()), st))
+    res.labels = torch.empty(max(mtot, 1), dtype=torch.int32, device=dev)[:mtot]
+    res.bin_K = torch.empty(B, dtype=torch.int32, device=dev)
+    res.bin_db = torch.empty((B, 8), dtype=torch.float64, device=dev)
+    ctx.check(ctx.lib.sctda_bin_cluster(ctx.handle, G, _lib.ptr(Xn), int(Xn.stride(0)), B, _lib.ptr(res.bin_off),
+                                        ctypes.c_void_p(res.members.data_ptr()), int(max_K), 0,
+                                        ctypes.c_void_p(res.labels.data_ptr()), _lib.ptr(res.bin_K), _lib.ptr(res.bin_db), st))
+    node_base = torch.empty(B + 1, dtype=torch.int32, device=dev)
+    ctx.check(ctx.lib.sctda_nodes_count(ctx.handle, B, _lib.ptr(res.bin_K), _lib.ptr(node_base), st))
+    V = int(node_base[B].item())
+    res.V = V
+    res.node_off = torch.empty(V + 1, dtype=torch.int32, device=dev)
+    res.node_members = torch.empty(max(mtot, 1), dtype=torch.int32, device=dev)[:mtot]
+    res.node_bin = torch.empty(max(V, 1), dtype=torch.int32, device=dev)[:V]
+    ctx.check(ctx.lib.sctda_nodes_fill(ctx.handle, B, _lib.ptr(res.bin_off), ctypes.c_void_p(res.members.data_ptr()),
+                                       ctypes.c_void_p(res.labels.data_ptr()), _lib.ptr(node_base), V,
+                                       _lib.ptr(res.node_off), ctypes.c_void_p(res.node_members.data_ptr()),
+                                       ctypes.c_void_p(res.node_bin.data_ptr()), st))
+    ecount = torch.zeros(1, dtype=torch.int64, device=dev)
+    ctx.check(ctx.lib.sctda_nerve_count(ctx.handle, N, V, _lib.ptr(res.node_off), ctypes.c_void_p(res.node_members.data_ptr()),
+                                        mtot, _lib.ptr(ecount), st))
+    E = int(ecount.item())
+    res.E = E
+    res.edges = torch.empty((max(E, 1), 2), dtype=torch.int32, device=dev)[:E]
+    if E:
+        ctx.check(ctx.lib.sctda_nerve_fill(ctx.handle, V, ctypes.c_void_p(res.edges.data_ptr()), st))
+    return res
+
+
+# ----------------------------------------------------------------------------------------------
+# the sakmapper-shaped API
+# ----------------------------------------------------------------------------------------------
+def _values(df):
+    return df.values if hasattr(df, 'values') else numpy.asarray(df)
+
+
+def apply_lens(df, lens='pca', metric='correlation', dissimilarity=None, device=0, **kwargs):
+    """sakmapper.apply_lens as called at ref:745-753.  Returns a DataFrame (N x 2, index of df).
+    'pca': the two leading principal components, computed on the device (sklearn.decomposition.PCA
+    sign convention); 'mds': the dissimilarity matrix in `metric` is computed on the device
+    (sctda_pairdist_rows_f64) and embedded by sklearn.manifold.MDS on the host (SMACOF is a
+    SURVEY.md §8f 'next' row); dissimilarity='precomputed' takes df itself as the matrix;
+    'neighbor': sklearn.manifold.SpectralEmbedding on the host."""
+    import pandas
+    X = numpy.asarray(_values(df), dtype=numpy.float64)
+    index = df.index if hasattr(df, 'index') else None
+    dev = torch.device('cuda', device)
+    if lens == 'pca':
+        if kwargs.get('n_components', 2) != 2:
+            raise ValueError('the lens is two-dimensional')
+        Xd = torch.from_numpy(numpy.ascontiguousarray(X)).to(dev)
+        out = pca_lens_device(Xd).cpu().numpy()
+    elif lens == 'mds':
+        import sklearn.manifold
+        if dissimilarity == 'precomputed':
+            D = X
+        else:
+            ctx = _lib.context(device)
+            D = pairwise_distances(ctx, _padded_device_table(X, dev), metric).cpu().numpy()
+            D = 0.5 * (D + D.T)
+        kw = dict(kwargs)
+        kw.setdefault('n_components', 2)
+        try:
+            out = sklearn.manifold.MDS(dissimilarity='precomputed', **kw).fit_transform(D)
+        except TypeError:
+            out = sklearn.manifold.MDS(metric='precomputed', **kw).fit_transform(D)
+    elif lens == 'neighbor':
+        import sklearn.manifold
+        kw = dict(kwargs)
+        kw.setdefault('n_components', 2)
+        out = sklearn.manifold.SpectralEmbedding(**kw).fit_transform(X)
+    else:
+        raise ValueError("lens must be 'pca', 'mds' or 'neighbor'")
+    return pandas.DataFrame(out, index=index)
+
+
+def pca_lens_device(Xd):
+    """Two leading principal component scores of the rows of Xd (device), with
+    sklearn.decomposition.PCA's sign rule (largest |loading| of each component positive).
+    Covariance eigen-decomposition through torch (library plumbing, not a hand-written kernel)."""
+    Xc = Xd - Xd.mean(dim=0, keepdim=True)
+    n, g = Xc.shape
+    if g <= n:
+        C = Xc.T @ Xc
+        w, v = torch.linalg.eigh(C)
+        comps = v[:, [-1, -2]].T                                   # [2, G]
+    else:
+        K = Xc @ Xc.T
+        w, u = torch.linalg.eigh(K)
+        u2 = u[:, [-1, -2]]
+        comps = (Xc.T @ u2).T
+        comps = comps / comps.norm(dim=1, keepdim=True)
+    idx = comps.abs().argmax(dim=1)
+    signs = torch.sign(comps[torch.arange(2, device=Xd.device), idx])
+    comps = comps * signs[:, None]
+    return Xc @ comps.T
+
+
+def mapper_graph(df, lens_data, resolution=10, gain=0.5, equalize=True, clust='agglomerative', stat='db', max_K=5,
+                 metric='euclidean', device=0, verbose=True):
+    """sakmapper.mapper_graph as called at ref:768-771 -> (G, all_clusters, patches):
+    G networkx.Graph with nodes 0..V-1 and weight-1.0 edges, all_clusters[k] the ascending row
+    positions of node k, patches {(i, j): row positions of cover patch (i, j)}.
+    `metric` (extension): distances used by the per-patch clustering."""
+    import networkx
+    if clust != 'agglomerative':
+        raise NotImplementedError("clust=%r: the device path clusters by single linkage ('agglomerative')" % (clust,))
+    ctx = _lib.context(device)
+    dev = torch.device('cuda', device)
+    Xd = _padded_device_table(_values(df), dev)
+    lens = numpy.asarray(_values(lens_data), dtype=numpy.float64)[:, :2]
+    res = build_graph_device(ctx, Xd, lens, resolution, gain, equalize=equalize, stat=stat, max_K=max_K, metric=metric)
+    bin_off = res.bin_off.cpu().numpy()
+    members = res.members.cpu().numpy()
+    node_off = res.node_off.cpu().numpy()
+    node_members = res.node_members.cpu().numpy()
+    edges = res.edges.cpu().numpy()
+    r = res.r
+    patches = {}
+    for b in range(r * r):
+        patches[(b // r, b % r)] = members[bin_off[b]:bin_off[b + 1]]
+    all_clusters = [node_members[node_off[k]:node_off[k + 1]] for k in range(res.V)]
+    if verbose:
+        print('total of %d patches required clustering' % int((bin_off[1:] > bin_off[:-1]).sum()))
+        print('this implies %d nodes in the mapper graph' % res.V)
+    G = networkx.Graph()
+    G.add_nodes_from(range(res.V))
+    G.add_edges_from(((int(i), int(j)) for i, j in edges), weight=1.0)
+    return G, all_clusters, patches
+
+
+class TopologicalRepresentation(object):
+    """Builds a topological representation of the data with the Mapper algorithm (ref:731-778)."""
+
+    def __init__(self, table, lens='mds', metric='correlation', precomputed=False, device=0, **kwargs):
+        """ref:735-756 (the scatter plot of ref:754-756 is not produced)."""
+        import pandas
+        self.device = device
+        self.metric = metric
+        self.df = pandas.read_table(table + '.mapper.tsv')                       # ref:743
+        if lens == 'neighbor':
+            self.lens_data_mds = apply_lens(self.df, lens=lens, device=device, **kwargs)
+        elif lens == 'mds':
+            if precomputed:
+                self.lens_data_mds = apply_lens(self.df, lens=lens, metric=metric, dissimilarity='precomputed',
+                                                device=device, **kwargs)
+            else:
+                self.lens_data_mds = apply_lens(self.df, lens=lens, metric=metric, device=device, **kwargs)
+        else:
+            self.lens_data_mds = apply_lens(self.df, lens=lens, device=device, **kwargs)
+
+    def save(self, name, resolution, gain, equalize=True, cluster='agglomerative', statistics='db', max_K=5,
+             cluster_metric='euclidean'):
+        """ref:758-778: writes name.json and name.gexf, returns the patches."""
+        G, all_clusters, patches = mapper_graph(self.df, lens_data=self.lens_data_mds, resolution=resolution, gain=gain,
+                                                equalize=equalize, clust=cluster, stat=statistics, max_K=max_K,
+                                                metric=cluster_metric, device=self.device)
+        formats.write_mapper_json(name + '.json', all_clusters)                  # ref:772-776
+        formats.write_gexf(name + '.gexf', G.number_of_nodes(), sorted(G.edges()))   # ref:777
+        return patches

@@ -1,0 +1,204 @@
+"""Parity of the CUDA Mapper path (through the C-ABI) with the CPU oracle
+(oracle/mapper_oracle.py; UNPINNED against the reference: sakmapper is absent).
+
+Bars: row normalisation, Gram matrices and distances BIT-EXACT (float64, fixed operation order:
+one fma chain over the features per element); cover memberships, cluster labels, node lists and
+edges EXACT (integers).  Needs a B200: `pytest -m gpu`."""
+import json
+import os
+
+import numpy
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip('torch')
+
+
+def _gpu():
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    from sctda_b200 import _lib
+    return _lib.context(0)
+
+
+def _data(n, g, seed):
+    from sctda_b200 import synth
+    X, t, _ = synth.expression_matrix(n, g, seed=seed)
+    Xc = X - X.mean(axis=0)
+    u, s, vt = numpy.linalg.svd(Xc, full_matrices=False)
+    return X, u[:, :2] * s[:2]
+
+
+def _bits(a):
+    return numpy.ascontiguousarray(a, dtype=numpy.float64).view(numpy.int64)
+
+
+@pytest.mark.parametrize('shape', [(70, 37), (300, 200), (129, 16), (5, 1001)])
+def test_row_normalize_and_gram_bit_exact(shape):
+    from oracle import mapper_oracle as mo
+    from sctda_b200 import mapper
+    ctx = _gpu()
+    n, g = shape
+    X, _ = _data(n, g, seed=n + g)
+    X[n // 2] = 1.5                                            # constant row
+    Xd = mapper._padded_device_table(X, torch.device('cuda', 0))
+    rng = numpy.random.RandomState(1)
+    ra = rng.randint(0, n, size=min(n, 150))
+    rb = rng.randint(0, n, size=min(n, 131))
+    for metric in ('euclidean', 'correlation'):
+        Xn_ref, sq_ref = mo.row_normalize(X, metric)
+        Xn, sq = mapper.row_normalize(ctx, Xd, metric)
+        assert (_bits(Xn.cpu().numpy()) == _bits(Xn_ref)).all()
+        assert (_bits(sq.cpu().numpy()) == _bits(sq_ref)).all()
+        G = mapper.gram_gather(ctx, Xn, ra, rb).cpu().numpy()
+        G_ref = mo.gram(Xn_ref, ra, rb)
+        numpy.testing.assert_allclose(G, G_ref, rtol=1e-13, atol=1e-13)
+        assert (_bits(G) == _bits(G_ref)).all(), 'DMMA result is not the sequential fma chain'
+
+
+@pytest.mark.parametrize('metric', ['euclidean', 'correlation'])
+def test_pairdist_rows(metric):
+    import scipy.spatial.distance as ssd
+    from oracle import mapper_oracle as mo
+    from sctda_b200 import mapper
+    ctx = _gpu()
+    X, _ = _data(333, 150, seed=2)
+    Xd = mapper._padded_device_table(X, torch.device('cuda', 0))
+    D = mapper.pairwise_distances(ctx, Xd, metric, row_block=100).cpu().numpy()
+    Xn, sq = mo.row_normalize(X, metric)
+    ref = mo.pairdist_rows(Xn, sq, 0, 333, metric)
+    assert (_bits(D) == _bits(ref)).all()
+    numpy.testing.assert_allclose(D, ssd.cdist(X, X, metric), rtol=1e-9, atol=1e-7)
+    assert (numpy.diag(D) == 0.0).all()
+
+
+def _device_result(ctx, X, lens, r, gain, equalize=True, metric='euclidean', max_K=5):
+    from sctda_b200 import mapper
+    Xd = mapper._padded_device_table(X, torch.device('cuda', 0))
+    return mapper.build_graph_device(ctx, Xd, lens, r, gain, equalize=equalize, max_K=max_K, metric=metric)
+
+
+@pytest.mark.parametrize('case', [(400, 60, 6, 0.4, True, 'euclidean', 5), (400, 60, 5, 2.0, False, 'euclidean', 5),
+                                  (900, 101, 9, 1.0, True, 'correlation', 5), (250, 40, 3, 0.3, True, 'euclidean', 8),
+                                  (120, 30, 1, 0.5, True, 'euclidean', 5)])
+def test_graph_identical_to_oracle(case):
+    from oracle import mapper_oracle as mo
+    ctx = _gpu()
+    n, g, r, gain, equalize, metric, max_K = case
+    X, lens = _data(n, g, seed=n + r)
+    lens[5] = lens[6]                                          # duplicate lens values
+    X[11] = X[10]                                              # duplicate cells (zero distances)
+    res = _device_result(ctx, X, lens, r, gain, equalize, metric, max_K)
+    bin_off = res.bin_off.cpu().numpy()
+    members = res.members.cpu().numpy()
+    labels = res.labels.cpu().numpy()
+    bin_K = res.bin_K.cpu().numpy()
+    bin_db = res.bin_db.cpu().numpy()
+    # stage by stage against the oracle
+    bins, _ = mo.cover(lens, r, gain, equalize)
+    Xn, _ = mo.row_normalize(X, metric)
+    for b, cells in enumerate(bins):
+        assert list(members[bin_off[b]:bin_off[b + 1]]) == list(cells), 'cover patch %d' % b
+        if len(cells) == 0:
+            assert bin_K[b] == 0
+            continue
+        lab, K, scores = mo.cluster_bin(mo.gram(Xn, cells, cells), max_K=max_K)
+        assert bin_K[b] == K, 'K of patch %d (%d cells): %r vs %r' % (b, len(cells), bin_db[b], scores)
+        assert list(labels[bin_off[b]:bin_off[b + 1]]) == list(lab)
+        if scores:
+            assert (_bits(bin_db[b, :len(scores)]) == _bits(numpy.array(scores))).all()
+    edges, clusters, _ = mo.mapper_graph(X, lens, r, gain, equalize=equalize, max_K=max_K, metric=metric)
+    node_off = res.node_off.cpu().numpy()
+    node_members = res.node_members.cpu().numpy()
+    assert res.V == len(clusters)
+    for k, c in enumerate(clusters):
+        assert list(node_members[node_off[k]:node_off[k + 1]]) == list(c)
+    assert [tuple(e) for e in res.edges.cpu().numpy().tolist()] == edges
+
+
+def test_topological_representation_files(tmp_path):
+    """The reference-facing classes end to end: .mapper.tsv -> TopologicalRepresentation.save ->
+    name.json / name.gexf -> UnrootedGraph (ref:735-778, 785-806)."""
+    _gpu()
+    import networkx
+    from oracle import mapper_oracle as mo
+    from sctda_b200 import formats, graph, mapper
+    X, _ = _data(300, 40, seed=4)
+    genes = ['G%02d' % i for i in range(40)]
+    base = str(tmp_path / 't')
+    with open(base + '.mapper.tsv', 'w') as f:
+        f.write('\t'.join(genes) + '\n')
+        for row in X:
+            f.write('\t'.join(formats.py2_str(v) for v in row) + '\n')
+    with open(base + '.all.tsv', 'w') as f:
+        f.write('ID\ttimepoint\tlib\t' + '\t'.join(genes) + '\n')
+        for i, row in enumerate(X):
+            f.write('D0_L_%d\t0\tL\t' % i + '\t'.join(formats.py2_str(v) for v in row) + '\n')
+    t = mapper.TopologicalRepresentation(base, lens='pca')
+    patches = t.save(base + '_g', 5, 0.5)
+    assert len(patches) == 25
+    import pandas
+    df = pandas.read_table(base + '.mapper.tsv')
+    lens = t.lens_data_mds.values
+    # the PCA lens agrees with sklearn (component signs included)
+    from sklearn.decomposition import PCA
+    numpy.testing.assert_allclose(lens, PCA(n_components=2).fit_transform(df.values), rtol=1e-7, atol=1e-8)
+    edges, clusters, _ = mo.mapper_graph(df.values, lens, 5, 0.5)
+    with open(base + '_g.json') as f:
+        dic = json.load(f)
+    assert dic == {str(k): [int(x) for x in c] for k, c in enumerate(clusters)}
+    g = networkx.read_gexf(base + '_g.gexf')
+    assert sorted((min(int(a), int(b)), max(int(a), int(b))) for a, b in g.edges()) == edges
+    assert all(d['weight'] == 1.0 for _, _, d in g.edges(data=True))
+    c = graph.UnrootedGraph(base + '_g', base + '.all.tsv', groups=False)
+    assert len(c.pl) >= 2 and c.connectivity('G00') >= 0.0
+    # MDS lens: the device dissimilarity feeds sklearn's MDS (ref:746-751)
+    t2 = mapper.TopologicalRepresentation(base, lens='mds', metric='correlation', random_state=0, n_init=1, max_iter=30)
+    assert t2.lens_data_mds.shape == (300, 2)
+
+
+def test_properties_at_scale():
+    """Invariants at a size the oracle does not reach in seconds."""
+    ctx = _gpu()
+    n, g, r, gain = 20000, 256, 20, 1.0
+    X, lens = _data(n, g, seed=9)
+    res = _device_result(ctx, X, lens, r, gain)
+    bin_off = res.bin_off.cpu().numpy().astype(numpy.int64)
+    members = res.members.cpu().numpy()
+    labels = res.labels.cpu().numpy()
+    bin_K = res.bin_K.cpu().numpy()
+    node_off = res.node_off.cpu().numpy().astype(numpy.int64)
+    node_members = res.node_members.cpu().numpy()
+    node_bin = res.node_bin.cpu().numpy()
+    edges = res.edges.cpu().numpy()
+    assert numpy.bincount(members, minlength=n).min() >= 1                     # every cell covered
+    sizes = bin_off[1:] - bin_off[:-1]
+    for b in range(r * r):
+        seg = members[bin_off[b]:bin_off[b + 1]]
+        assert (numpy.diff(seg) > 0).all()                                      # ascending, no duplicates
+        if sizes[b] >= 2:
+            assert 2 <= bin_K[b] <= 5
+            assert set(labels[bin_off[b]:bin_off[b + 1]]) == set(range(bin_K[b]))
+    assert node_off[-1] == bin_off[-1] == len(node_members)                     # nodes partition the patches
+    assert res.V == bin_K.sum()
+    sets = [set(node_members[node_off[k]:node_off[k + 1]].tolist()) for k in range(res.V)]
+    for b in range(r * r):
+        ks = numpy.nonzero(node_bin == b)[0]
+        if len(ks):
+            assert set().union(*[sets[k] for k in ks]) == set(members[bin_off[b]:bin_off[b + 1]].tolist())
+    # nerve: sorted, i < j, exactly the intersecting pairs (checked through a cell -> nodes index)
+    assert (edges[:, 0] < edges[:, 1]).all()
+    assert (numpy.lexsort((edges[:, 1], edges[:, 0])) == numpy.arange(len(edges))).all()
+    brute = set()
+    owner = [[] for _ in range(n)]
+    for k in range(res.V):
+        for c in node_members[node_off[k]:node_off[k + 1]]:
+            owner[c].append(k)
+    for lst in owner:
+        for x in range(len(lst)):
+            for y in range(x + 1, len(lst)):
+                brute.add((min(lst[x], lst[y]), max(lst[x], lst[y])))
+    assert set(map(tuple, edges.tolist())) == brute
+    # nodes of one patch never connect
+    assert (node_bin[edges[:, 0]] != node_bin[edges[:, 1]]).all()
