@@ -49,6 +49,12 @@ def parse():
     ap.add_argument('--cells', type=int, default=20000)
     ap.add_argument('--nodes', type=int, default=2000)
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-mapper', action='store_true')
+    ap.add_argument('--mapper-cells', type=int, default=20000)
+    ap.add_argument('--mapper-genes', type=int, default=5000)
+    ap.add_argument('--mapper-resolution', type=int, default=30)
+    ap.add_argument('--mapper-gain', type=float, default=3.0)
+    ap.add_argument('--mapper-metric', default='correlation')
     ap.add_argument('--no-cpu', action='store_true')
     return ap.parse_args()
 
@@ -190,6 +196,86 @@ def run_reference(a):
 
 
 # ---------------------------------------------------------------------------------------------
+# Mapper build (BASELINE.json configs[1]: 20k cells x 5k genes, correlation metric, PCA lens,
+# resolution 30, gain 3, one B200) — reported inside the same JSON line under "mapper"
+# ---------------------------------------------------------------------------------------------
+def fp64_probe_tflops(dev):
+    """cuBLAS DGEMM yard-stick for the FP64 tensor pipe (MEASURED_PEAKS.json has no FP64 figure):
+    torch.matmul on 6144^3 float64, best of 5, CUDA events."""
+    import torch
+    n = 6144
+    A = torch.randn((n, n), dtype=torch.float64, device=dev)
+    B = torch.randn((n, n), dtype=torch.float64, device=dev)
+    best = 0.0
+    for _ in range(6):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(A, B)
+        e1.record()
+        torch.cuda.synchronize()
+        best = max(best, 2.0 * n ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    return best
+
+
+def run_mapper(a, ctx, dev, steps, warmup):
+    import torch
+    from sctda_b200 import mapper, synth
+    N, G, r, gain = a.mapper_cells, a.mapper_genes, a.mapper_resolution, a.mapper_gain
+    X = synth.expression_genes_torch(G, N, seed=synth.SEED + 11, device=dev).T.contiguous()      # cells x genes
+    t0 = time.perf_counter()
+    lens = mapper.pca_lens_device(X)
+    torch.cuda.synchronize()
+    lens_ms = 1e3 * (time.perf_counter() - t0)
+    prof = {}
+    for _ in range(max(1, warmup)):
+        mapper.build_graph_device(ctx, X, lens, r, gain, metric=a.mapper_metric, profile=prof)
+    times, gemm = [], []
+    for _ in range(steps):
+        prof = {}
+        res = mapper.build_graph_device(ctx, X, lens, r, gain, metric=a.mapper_metric, profile=prof)
+        times.append(prof['total_ms'])
+        gemm.append(prof['gemm_ms'])
+    bin_off = res.bin_off.cpu().numpy().astype(numpy.int64)
+    m = bin_off[1:] - bin_off[:-1]
+    sum_m2 = float((m * m).sum())
+    flops = 2.0 * G * sum_m2                                   # SURVEY.md §8d: intra-patch tiles, no symmetry credit
+    ms = float(numpy.mean(times))
+    gms = float(numpy.mean(gemm))
+    peak = fp64_probe_tflops(dev)
+    out = {'metric': 'Mapper build cells/s', 'value': N / (ms * 1e-3), 'unit': 'cells/s', 'ms_per_build': ms,
+           'config': {'workload': 'Mapper build: %d cells x %d genes, %s metric, PCA lens, resolution %d, gain %g, '
+                                  'max_K 5, 1 B200' % (N, G, a.mapper_metric, r, gain),
+                      'cover_multiplicity': float(prof['Mtot']) / N, 'nodes': prof['V'], 'edges': prof['E'],
+                      'largest_patch': int(m.max()), 'sum_m2': sum_m2},
+           'stages_ms': {k[:-3]: round(float(v), 3) for k, v in prof.items()
+                         if k.endswith('_ms') and k not in ('total_ms', 'gemm_ms')},
+           'pca_lens_ms_untimed': lens_ms,
+           'roofline': {'bound': 'tensor', 'achieved': flops / (gms * 1e-3) / 1e12, 'peak': peak, 'unit': 'TFLOP/s',
+                        'frac': flops / (gms * 1e-3) / 1e12 / peak, 'traffic': None, 'kernel': 'gemm_kernel (FP64 DMMA)',
+                        'kernel_ms': gms, 'flops': flops,
+                        'peak_source': 'torch.matmul float64 6144^3 (cuBLAS DGEMM) probe in this run'}}
+    del X
+    torch.cuda.empty_cache()
+    return out
+
+
+def mapper_cpu_sample():
+    """The Mapper oracle on BASELINE.json configs[0] scale (1,000 cells x 2,000 genes, r=20, gain 2)."""
+    from oracle import mapper_oracle as mo
+    from sctda_b200 import synth
+    X = synth.expression_genes_numpy(2000, 1000, seed=synth.SEED + 11).T.copy()
+    Xc = X - X.mean(axis=0)
+    u, s_, _ = numpy.linalg.svd(Xc, full_matrices=False)
+    lens = u[:, :2] * s_[:2]
+    t0 = time.perf_counter()
+    edges, clusters, _ = mo.mapper_graph(X, lens, 20, 2.0, metric='correlation')
+    dt = time.perf_counter() - t0
+    return {'value': 1000 / dt, 'unit': 'cells/s', 'cores': os.cpu_count(), 'kind': 'port',
+            'sample': 'oracle/mapper_oracle.py on 1,000 cells x 2,000 genes, r=20, gain 2 (%d nodes, %d edges), %.1f s; '
+                      'Gram matrices by an OpenMP fma loop, the rest single-threaded numpy' % (len(clusters), len(edges), dt)}
+
+
+# ---------------------------------------------------------------------------------------------
 # own arm
 # ---------------------------------------------------------------------------------------------
 def run_own(a):
@@ -243,10 +329,8 @@ def run_own(a):
         barrier()
         ms = e0.elapsed_time(e1)
     launches = ctx.launch_count() - l0
-    # the dominant kernel alone (events recorded by the library around conn_perm_kernel)
-    for _ in range(min(a.steps, 3)):
-        step()
-        kernel_ms.append(ctx.last_kernel_ms())
+    # the dominant kernel alone (events recorded by the library around conn_perm_kernel, last timed step)
+    kernel_ms.append(ctx.last_kernel_ms())
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -266,8 +350,9 @@ def run_own(a):
         torch.cuda.empty_cache()
         graph.conn_perm_test_host(ctx, dg, Yh, Ph, Oh, log2=True)       # warm-up (allocations)
         barrier()
+        e2e_steps = min(a.steps, 2)
         e0.record()
-        for _ in range(a.steps):
+        for _ in range(e2e_steps):
             counts = graph.conn_perm_test_host(ctx, dg, Yh, Ph, Oh, log2=True)
         e1.record()
         barrier()
@@ -275,9 +360,9 @@ def run_own(a):
         if world > 1:
             dist.all_reduce(t2, op=dist.ReduceOp.MAX)
         assert int(counts.sum()) >= 0
-        e2e = {'value': total_units / (float(t2.item()) * 1e-3), 'unit': UNIT,
+        e2e = {'value': float(a.genes) * a.perms * e2e_steps / (float(t2.item()) * 1e-3), 'unit': UNIT, 'steps': e2e_steps,
                'h2d_bytes_per_step': int(Yh.numel() * 8 + Ph.numel() * 4 + Oh.numel() * 8),
-               'd2h_bytes_per_step': int(counts.numel() * 4), 'ms_per_step': float(t2.item()) / a.steps}
+               'd2h_bytes_per_step': int(counts.numel() * 4), 'ms_per_step': float(t2.item()) / e2e_steps}
 
     # ---- roofline of the dominant kernel ----
     peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
@@ -300,6 +385,16 @@ def run_own(a):
             'note': 'permutation block shared by all genes: index traffic is amortised over the gene shard, '
                     'the binding resource is the L2->SM gather of 8*Mtot bytes per gene*perm (DESIGN.md)'}
 
+    mapper_line = None
+    if rank == 0 and not a.no_mapper:
+        if not a.no_e2e:
+            del Yh, Ph
+        else:
+            del Y, perms
+        torch.cuda.empty_cache()
+        mapper_line = run_mapper(a, ctx, dev, max(1, min(a.steps, 3)), 2)
+        if world == 1 and not a.no_cpu:
+            mapper_line['cpu_baseline'] = mapper_cpu_sample()
     if rank == 0:
         cpu = None
         if world == 1 and not a.no_cpu:
@@ -310,7 +405,7 @@ def run_own(a):
                 'warmup': a.warmup, 'ms_per_step': ms_max / a.steps, 'higher_is_better': True, 'scaling': 'strong',
                 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': workload_config(a, world),
                 'clocks': clocks.summary(), 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roof,
-                'cpu_baseline': cpu, 'tie_genes': int((ties > 0).sum().item())}
+                'cpu_baseline': cpu, 'tie_genes': int((ties > 0).sum().item()), 'mapper': mapper_line}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

@@ -107,8 +107,11 @@ class Context(object):
     def launch_count(self):
         return int(self.lib.sctda_launch_count(self.handle))
 
+    timing_enabled = False
+
     def set_kernel_timing(self, enabled=True):
         self.check(self.lib.sctda_set_kernel_timing(self.handle, 1 if enabled else 0))
+        self.timing_enabled = bool(enabled)
 
     def last_kernel_ms(self):
         ms = ctypes.c_float()

@@ -103,7 +103,7 @@ class MapperDeviceResult(object):
 
 
 def build_graph_device(ctx, Xd, lens, resolution, gain, equalize=True, stat='db', max_K=5, metric='euclidean',
-                       bounds=None):
+                       bounds=None, profile=None):
     """normalise -> cover -> per-patch clustering -> nodes -> nerve, everything on the device.
     Xd: [N, G] float64 device tensor (even leading dimension); lens: [N, 2] host or device."""
     dev = Xd.device
@@ -118,7 +118,16 @@ def build_graph_device(ctx, Xd, lens, resolution, gain, equalize=True, stat='db'
         bounds = cover_bounds(lens_d.cpu().numpy(), r, gain, equalize)
     b = [torch.from_numpy(numpy.ascontiguousarray(x)).to(dev) for x in bounds]
     st = _stream(dev)
+    marks = []
+
+    def mark(name):
+        if profile is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record(torch.cuda.current_stream(dev))
+            marks.append((name, e))
+    mark('start')
     Xn, _ = row_normalize(ctx, Xd, metric)
+    mark('normalize')
     res = MapperDeviceResult()
     res.r = r
     B = r * r
@@ -128,12 +137,101 @@ def build_graph_device(ctx, Xd, lens, resolution, gain, equalize=True, stat='db'
     mtot = int(res.bin_off[B].item())
     res.members = torch.empty(max(mtot, 1), dtype=torch.int32, device=dev)[:mtot]
     ctx.check(ctx.lib.sctda_cover_fill(ctx.handle, N, r, _lib.ptr(res.bin_off), ctypes.c_void_p(res.members.data_ptr()), st))
+    mark('cover')
     res.labels = torch.empty(max(mtot, 1), dtype=torch.int32, device=dev)[:mtot]
     res.bin_K = torch.empty(B, dtype=torch.int32, device=dev)
     res.bin_db = torch.empty((B, 8), dtype=torch.float64, device=dev)
     ctx.check(ctx.lib.sctda_bin_cluster(ctx.handle, G, _lib.ptr(Xn), int(Xn.stride(0)), B, _lib.ptr(res.bin_off),
                                         ctypes.c_void_p(res.members.data_ptr()), int(max_K), 0,
                                         ctypes.c_void_p(res.labels.data_ptr()), _lib.ptr(res.bin_K), _lib.ptr(res.bin_db), st))
+    if profile is not None:
+        profile['gemm_ms'] = ctx.last_kernel_ms() if ctx.timing_enabled else None
+    mark('cluster')
+    node_base = torch.empty(B + 1, dtype=torch.int32, device=dev)
+    ctx.check(ctx.lib.sctda_nodes_count(ctx.handle, B, _lib.ptr(res.bin_K), _lib.ptr(node_base), st))
+    V = int(node_base[B].item())
+    res.V = V
+    res.node_off = torch.empty(V + 1, dtype=torch.int32, device=dev)
+    res.node_members = torch.empty(max(mtot, 1), dtype=torch.int32, device=dev)[:mtot]
+    res.node_bin = torch.empty(max(V, 1), dtype=torch.int32, device=dev)[:V]
+    ctx.check(ctx.lib.sctda_nodes_fill(ctx.handle, B, _lib.ptr(res.bin_off), ctypes.c_void_p(res.members.data_ptr()),
+                                       ctypes.c_void_p(res.labels.data_ptr()), _lib.ptr(node_base), V,
+                                       _lib.ptr(res.node_off), ctypes.c_void_p(res.node_members.data_ptr()),
+                                       ctypes.c_void_p(res.node_bin.data_ptr()), st))
+    mark('nodes')
+    ecount = torch.zeros(1, dtype=torch.int64, device=dev)
+    ctx.check(ctx.lib.sctda_nerve_count(ctx.handle, N, V, _lib.ptr(res.node_off), ctypes.c_void_p(res.node_members.data_ptr()),
+                                        mtot, _lib.ptr(ecount), st))
+    E = int(ecount.item())
+    res.E = E
+    res.edges = torch.empty((max(E, 1), 2), dtype=torch.int32, device=dev)[:E]
+    if E:
+        ctx.check(ctx.lib.sctda_nerve_fill(ctx.handle, V, ctypes.c_void_p(res.edges.data_ptr()), st))
+    mark('nerve')
+    if profile is not None:
+        torch.cuda.current_stream(dev).synchronize()
+        for (_, e0), (name, e1) in zip(marks[:-1], marks[1:]):
+            profile[name + '_ms'] = e0.elapsed_time(e1)
+        profile['total_ms'] = marks[0][1].elapsed_time(marks[-1][1])
+        profile['Mtot'] = mtot
+        profile['V'] = V
+        profile['E'] = E
+    return res
+
+
+def cluster_sub_csr(ctx, Xn, sub_off, sub_members, max_K=5):
+    """sctda_bin_cluster on a sub-CSR given as host arrays; returns host (labels, K)."""
+    dev = Xn.device
+    nb = len(sub_off) - 1
+    off_d = torch.as_tensor(numpy.asarray(sub_off, dtype=numpy.int32)).to(dev)
+    mem_d = torch.as_tensor(numpy.asarray(sub_members, dtype=numpy.int32)).to(dev)
+    m = int(mem_d.numel())
+    labels = torch.zeros(max(m, 1), dtype=torch.int32, device=dev)
+    K = torch.zeros(max(nb, 1), dtype=torch.int32, device=dev)
+    if nb:
+        ctx.check(ctx.lib.sctda_bin_cluster(ctx.handle, int(Xn.shape[1]), _lib.ptr(Xn), int(Xn.stride(0)), nb, _lib.ptr(off_d),
+                                            ctypes.c_void_p(mem_d.data_ptr()), int(max_K), 0, _lib.ptr(labels), _lib.ptr(K), None,
+                                            _stream(dev)))
+    return labels[:m].cpu().numpy(), K[:nb].cpu().numpy()
+
+
+def build_graph_distributed(ctx, Xd, lens, resolution, gain, equalize=True, max_K=5, metric='euclidean'):
+    """The graph build with the per-patch clustering sharded over the ranks of the default
+    process group: X and the lens are replicated, patches are dealt by
+    descending m^2, labels are exchanged by one all_gather, cover / nodes / nerve are replicated.
+    Returns the same MapperDeviceResult on every rank."""
+    from . import parallel
+    dev = Xd.device
+    N, G = Xd.shape
+    r = int(resolution)
+    B = r * r
+    lens_h = lens.cpu().numpy() if isinstance(lens, torch.Tensor) else numpy.array(lens, dtype=numpy.float64)
+    lens_d = torch.as_tensor(lens_h, dtype=torch.float64).to(dev).contiguous()
+    b = [torch.from_numpy(numpy.ascontiguousarray(x)).to(dev) for x in cover_bounds(lens_h, r, gain, equalize)]
+    st = _stream(dev)
+    Xn, _ = row_normalize(ctx, Xd, metric)
+    res = MapperDeviceResult()
+    res.r = r
+    res.bin_off = torch.empty(B + 1, dtype=torch.int32, device=dev)
+    ctx.check(ctx.lib.sctda_cover_count(ctx.handle, N, _lib.ptr(lens_d), 2, r, _lib.ptr(b[0]), _lib.ptr(b[1]),
+                                        _lib.ptr(b[2]), _lib.ptr(b[3]), _lib.ptr(res.bin_off), st))
+    bin_off = res.bin_off.cpu().numpy()
+    mtot = int(bin_off[B])
+    res.members = torch.empty(max(mtot, 1), dtype=torch.int32, device=dev)[:mtot]
+    ctx.check(ctx.lib.sctda_cover_fill(ctx.handle, N, r, _lib.ptr(res.bin_off), ctypes.c_void_p(res.members.data_ptr()), st))
+    labels, bin_K = parallel.patch_sharded_labels(bin_off, res.members.cpu().numpy(),
+                                                  lambda so, sm: cluster_sub_csr(ctx, Xn, so, sm, max_K))
+    res.labels = torch.as_tensor(labels).to(dev)
+    res.bin_K = torch.as_tensor(bin_K).to(dev)
+    res.bin_db = None
+    _finish_nodes_and_nerve(ctx, res, N, mtot)
+    return res
+
+
+def _finish_nodes_and_nerve(ctx, res, N, mtot):
+    dev = res.bin_off.device
+    st = _stream(dev)
+    B = res.r * res.r
     node_base = torch.empty(B + 1, dtype=torch.int32, device=dev)
     ctx.check(ctx.lib.sctda_nodes_count(ctx.handle, B, _lib.ptr(res.bin_K), _lib.ptr(node_base), st))
     V = int(node_base[B].item())
@@ -148,12 +246,10 @@ def build_graph_device(ctx, Xd, lens, resolution, gain, equalize=True, stat='db'
     ecount = torch.zeros(1, dtype=torch.int64, device=dev)
     ctx.check(ctx.lib.sctda_nerve_count(ctx.handle, N, V, _lib.ptr(res.node_off), ctypes.c_void_p(res.node_members.data_ptr()),
                                         mtot, _lib.ptr(ecount), st))
-    E = int(ecount.item())
-    res.E = E
-    res.edges = torch.empty((max(E, 1), 2), dtype=torch.int32, device=dev)[:E]
-    if E:
+    res.E = int(ecount.item())
+    res.edges = torch.empty((max(res.E, 1), 2), dtype=torch.int32, device=dev)[:res.E]
+    if res.E:
         ctx.check(ctx.lib.sctda_nerve_fill(ctx.handle, V, ctypes.c_void_p(res.edges.data_ptr()), st))
-    return res
 
 
 # ----------------------------------------------------------------------------------------------

@@ -1,0 +1,123 @@
+"""world_size-2 gloo tests of the multi-GPU host logic (sctda_b200/parallel.py): gene shards of
+the permutation test and patch shards of the Mapper build reassemble to the single-rank result.
+The per-rank compute is the CPU oracle here (tests may use it); on the box it is the CUDA path."""
+import os
+import socket
+
+import numpy
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, ws, port, fn, out_dir):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=ws)
+    try:
+        res = fn(rank, ws)
+        numpy.save(os.path.join(out_dir, 'r%d.npy' % rank), numpy.asarray(res, dtype=numpy.int64))
+    finally:
+        dist.destroy_process_group()
+
+
+def _run(fn, out_dir, ws=2):
+    mp.spawn(_worker, args=(ws, _free_port(), fn, str(out_dir)), nprocs=ws, join=True)
+    return [numpy.load(os.path.join(str(out_dir), 'r%d.npy' % r)) for r in range(ws)]
+
+
+def _conn_case():
+    from oracle import conn_oracle as co
+    from sctda_b200 import synth
+    members, adj, Y = synth.connectivity_case(300, 30, 11, seed=21)
+    st = co.GraphState([str(k) for k in range(30)], adj.toarray(), {str(k): [int(c) for c in members[k]] for k in range(30)},
+                       {'g%d' % i: Y[i] for i in range(11)})
+    perms = co.perm_indices(24, 300, numpy.random.RandomState(3))
+    return co, st, perms
+
+
+def _conn_fn(rank, ws):
+    from sctda_b200 import parallel
+    co, st, perms = _conn_case()
+
+    def compute(lo, hi):
+        with numpy.errstate(invalid='ignore', divide='ignore'):
+            return torch.tensor([int(round(24 * co.connectivity_pvalue(st, 'g%d' % i, n=24, perms=perms))) for i in range(lo, hi)],
+                                dtype=torch.int32)
+    return parallel.gene_sharded_counts(11, compute).numpy()
+
+
+def test_gene_shards_reassemble(tmp_path):
+    co, st, perms = _conn_case()
+    with numpy.errstate(invalid='ignore', divide='ignore'):
+        ref = [int(round(24 * co.connectivity_pvalue(st, 'g%d' % i, n=24, perms=perms))) for i in range(11)]
+    outs = _run(_conn_fn, tmp_path)
+    for o in outs:
+        assert list(o) == ref
+
+
+def _mapper_case():
+    from oracle import mapper_oracle as mo
+    from sctda_b200 import synth
+    X, _, _ = synth.expression_matrix(260, 30, seed=5)
+    Xc = X - X.mean(axis=0)
+    u, s, _ = numpy.linalg.svd(Xc, full_matrices=False)
+    lens = u[:, :2] * s[:2]
+    bins, _ = mo.cover(lens, 5, 0.6, True)
+    off = numpy.concatenate([[0], numpy.cumsum([len(b) for b in bins])])
+    members = numpy.concatenate(bins)
+    Xn, _ = mo.row_normalize(X, 'euclidean')
+    return mo, Xn, off, members
+
+
+def _cluster_sub(mo, Xn, sub_off, sub_members):
+    labels, K = [], []
+    for i in range(len(sub_off) - 1):
+        cells = sub_members[sub_off[i]:sub_off[i + 1]]
+        if len(cells) == 0:
+            K.append(0)
+            continue
+        lab, k, _ = mo.cluster_bin(mo.gram(Xn, cells, cells))
+        labels += list(lab)
+        K.append(k)
+    return numpy.array(labels, dtype=numpy.int32), numpy.array(K, dtype=numpy.int32)
+
+
+def _mapper_fn(rank, ws):
+    from sctda_b200 import parallel
+    mo, Xn, off, members = _mapper_case()
+    labels, K = parallel.patch_sharded_labels(off, members, lambda so, sm: _cluster_sub(mo, Xn, so, sm))
+    return numpy.concatenate([labels, K])
+
+
+def test_patch_shards_reassemble(tmp_path):
+    mo, Xn, off, members = _mapper_case()
+    labels, K = _cluster_sub(mo, Xn, off, members)
+    outs = _run(_mapper_fn, tmp_path)
+    for o in outs:
+        assert list(o) == list(labels) + list(K)
+
+
+def test_lpt_assignment_and_shards():
+    from sctda_b200 import parallel
+    sizes = [5, 0, 100, 7, 7, 50, 0, 49, 1]
+    parts = parallel.assign_patches_lpt(sizes, 3)
+    assert sorted(numpy.concatenate(parts).tolist()) == list(range(9))
+    loads = [sum(sizes[b] ** 2 for b in p) for p in parts]
+    assert max(loads) == 100 ** 2                      # the largest patch alone on its rank
+    assert parallel.assign_patches_lpt(sizes, 3)[0].tolist() == parts[0].tolist()   # deterministic
+    assert [parallel.shard_range(10, r, 4) for r in range(4)] == [(0, 2), (2, 5), (5, 7), (7, 10)]
+    off = numpy.array([0, 2, 2, 5])
+    so, sm = parallel.sub_csr(off, numpy.array([9, 8, 7, 6, 5]), numpy.array([0, 2]))
+    assert so.tolist() == [0, 2, 5] and sm.tolist() == [9, 8, 7, 6, 5]
+    so, sm = parallel.sub_csr(off, numpy.array([9, 8, 7, 6, 5]), numpy.array([1]))
+    assert so.tolist() == [0, 0] and sm.tolist() == []
