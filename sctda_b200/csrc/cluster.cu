@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(1024) scan_kernel(const int32_t* __restrict__ 
     const int64_t per = (n + 1023) / 1024;
     const int64_t lo = (int64_t)t * per, hi = lo + per < n ? lo + per : n;
     auto f = [map](int32_t v) -> long long {
-        if (map == MAP_TILES) { long long q = (v + 127) / 128; return q * q; }
+        if (map == MAP_TILES) { long long q = (v + 127) / 128; return q * (q + 1) / 2; }   // upper-triangular tiles
         if (map == MAP_SQUARE) return (long long)v * v;
         return v;
     };
@@ -129,8 +129,8 @@ struct ClusterArgs {
     int32_t* mst_order;       // [Mtot] insertion step of vertex u (-1 for the root)
     int32_t* mst_seq;         // [Mtot] vertex inserted at step t (seq[0] = 0)
     double* T;                // [Mtot][kMaxK] column sums of the finest partition
+    double* TK;               // [Mtot][kMaxK] column sums of the level under evaluation
     double* dist;             // [Mtot] scratch
-    int8_t* lev;              // [kMaxK-1][Mtot] labels of the partition with L+1 edges removed
     int32_t* labels;          // out [Mtot]
     int32_t* bin_K;           // out [nbins]
     double* bin_db;           // out [nbins][kMaxK] Davies-Bouldin score of K = 2.. (NaN where not evaluated)
@@ -204,7 +204,25 @@ __global__ void __launch_bounds__(256) prim_kernel(ClusterArgs a) {
 // ---------------------------------------------------------------------------------------------
 // cut + Davies-Bouldin model selection per patch
 // ---------------------------------------------------------------------------------------------
+// Sum over p ascending of (lab[p] == I ? v[p*stride] : 0.0): the masked terms add +0.0, an exact
+// no-op, so this is the sequential sum over the members of cluster I; the loads do not depend on
+// the running sum and are issued eight at a time.
+__device__ __forceinline__ double masked_seq_sum(const double* __restrict__ v, int stride, const int8_t* lab, int I, int m) {
+    double acc = 0.0;
+    int p = 0;
+    for (; p + 8 <= m; p += 8) {
+        double x[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) x[u] = (lab[p + u] == I) ? v[(int64_t)(p + u) * stride] : 0.0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc = __dadd_rn(acc, x[u]);
+    }
+    for (; p < m; ++p) acc = __dadd_rn(acc, (lab[p] == I) ? v[(int64_t)p * stride] : 0.0);
+    return acc;
+}
+
 __global__ void __launch_bounds__(256) select_kernel(ClusterArgs a) {
+    extern __shared__ __align__(16) unsigned char s_dyn[];      // labels of every level: int8 [nlev][m]
     __shared__ double s_rk[8];
     __shared__ int s_ri[8], s_ro[8];
     __shared__ int s_heavy[kMaxK];               // vertices whose edge is the h-th heaviest
@@ -227,7 +245,7 @@ __global__ void __launch_bounds__(256) select_kernel(ClusterArgs a) {
     const int32_t* ord = a.mst_order + off;
     const int32_t* par = a.mst_parent + off;
     const int32_t* seq = a.mst_seq + off;
-    const int64_t Mtot = a.bin_off[a.nbins];
+    int8_t* lev = (int8_t*)s_dyn;
     // (c) the nlev heaviest tree edges: (weight desc, insertion order desc)
     for (int h = 0; h < nlev; ++h) {
         double bk = -1.0;
@@ -262,7 +280,7 @@ __global__ void __launch_bounds__(256) select_kernel(ClusterArgs a) {
     //     earlier).  Components are then renumbered by their smallest vertex.
     if (tid < nlev) {
         const int L = tid;
-        int8_t* lab = a.lev + (int64_t)L * Mtot + off;
+        int8_t* lab = lev + (size_t)L * m;
         int ncomp = 1;
         int cmin[kMaxK];
         cmin[0] = 0;
@@ -288,68 +306,79 @@ __global__ void __launch_bounds__(256) select_kernel(ClusterArgs a) {
     }
     __syncthreads();
     const int F = kmax;                                        // clusters of the finest level
-    const int8_t* fine = a.lev + (int64_t)(nlev - 1) * Mtot + off;
+    const int8_t* fine = lev + (size_t)(nlev - 1) * m;
+    double* T = a.T + (int64_t)off * kMaxK;                    // [m][kMaxK]
+    double* TK = a.TK + (int64_t)off * kMaxK;                  // [m][kMaxK], per level
+    double* dist = a.dist + off;
     // (e) T[p][f] = sum over q ascending of G[q][p] for q in fine cluster f
     for (int p = tid; p < m; p += 256) {
         double acc[kMaxK];
 #pragma unroll
         for (int f = 0; f < kMaxK; ++f) acc[f] = 0.0;
-        for (int q = 0; q < m; ++q) {
+        int q = 0;
+        for (; q + 4 <= m; q += 4) {
+            double g[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) g[u] = Gm[(int64_t)(q + u) * m + p];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int fq = fine[q + u];                    // uniform across the CTA
+#pragma unroll
+                for (int f = 0; f < kMaxK; ++f)
+                    if (fq == f) acc[f] = __dadd_rn(acc[f], g[u]);
+            }
+        }
+        for (; q < m; ++q) {
             const double g = Gm[(int64_t)q * m + p];
-            const int fq = fine[q];                            // uniform across the CTA
+            const int fq = fine[q];
 #pragma unroll
             for (int f = 0; f < kMaxK; ++f)
                 if (fq == f) acc[f] = __dadd_rn(acc[f], g);
         }
 #pragma unroll
-        for (int f = 0; f < kMaxK; ++f) a.T[(int64_t)(off + p) * kMaxK + f] = acc[f];
+        for (int f = 0; f < kMaxK; ++f) T[(int64_t)p * kMaxK + f] = acc[f];
     }
     __syncthreads();
     // (f) Davies-Bouldin index of every level
     for (int L = 0; L < nlev; ++L) {
         const int K = L + 2;
-        const int8_t* lab = a.lev + (int64_t)L * Mtot + off;
+        const int8_t* lab = lev + (size_t)L * m;
         if (tid < F) s_cof[tid] = lab[s_fine_rep[tid]];
         __syncthreads();
+        for (int p = tid; p < m; p += 256) {                    // TK[p][J] = sum_{f in J, ascending} T[p][f]
+            double tk[kMaxK];
+#pragma unroll
+            for (int J = 0; J < kMaxK; ++J) tk[J] = 0.0;
+            for (int f = 0; f < F; ++f) {
+                const double t = T[(int64_t)p * kMaxK + f];
+                const int J = s_cof[f];
+#pragma unroll
+                for (int j2 = 0; j2 < kMaxK; ++j2)
+                    if (J == j2) tk[j2] = __dadd_rn(tk[j2], t);
+            }
+#pragma unroll
+            for (int J = 0; J < kMaxK; ++J) TK[(int64_t)p * kMaxK + J] = tk[J];
+        }
         if (tid < K) {                                          // cluster sizes
             int n = 0;
             for (int p = 0; p < m; ++p) n += (lab[p] == tid);
             s_n[tid] = (double)n;
         }
-        if (tid >= 32 && tid < 32 + K * K) {                    // c_I . c_J
-            const int I = (tid - 32) / K, J = (tid - 32) % K;
-            double acc = 0.0;
-            for (int p = 0; p < m; ++p) {
-                if (lab[p] != I) continue;
-                double tk = 0.0;
-                for (int f = 0; f < F; ++f)
-                    if (s_cof[f] == J) tk = __dadd_rn(tk, a.T[(int64_t)(off + p) * kMaxK + f]);
-                acc = __dadd_rn(acc, tk);
-            }
-            s_cc[I][J] = acc;
-        }
         __syncthreads();
-        if (tid < K * K) {
+        if (tid < K * K) {                                      // c_I . c_J, one thread per pair
             const int I = tid / K, J = tid % K;
-            s_cc[I][J] = __ddiv_rn(s_cc[I][J], __dmul_rn(s_n[I], s_n[J]));
+            const double acc = masked_seq_sum(TK + J, kMaxK, lab, I, m);
+            s_cc[I][J] = __ddiv_rn(acc, __dmul_rn(s_n[I], s_n[J]));
         }
         __syncthreads();
         for (int p = tid; p < m; p += 256) {                    // |x_p - c_I|
             const int I = lab[p];
-            double tk = 0.0;
-            for (int f = 0; f < F; ++f)
-                if (s_cof[f] == I) tk = __dadd_rn(tk, a.T[(int64_t)(off + p) * kMaxK + f]);
-            const double xc = __ddiv_rn(tk, s_n[I]);
+            const double xc = __ddiv_rn(TK[(int64_t)p * kMaxK + I], s_n[I]);
             const double d2 = fmax(__dadd_rn(fma(-2.0, xc, Gm[(int64_t)p * m + p]), s_cc[I][I]), 0.0);
-            a.dist[off + p] = sqrt(d2);
+            dist[p] = sqrt(d2);
         }
         __syncthreads();
-        if (tid < K) {
-            double acc = 0.0;
-            for (int p = 0; p < m; ++p)
-                if (lab[p] == tid) acc = __dadd_rn(acc, a.dist[off + p]);
-            s_S[tid] = __ddiv_rn(acc, s_n[tid]);
-        }
+        if (tid < K) s_S[tid] = __ddiv_rn(masked_seq_sum(dist, 1, lab, tid, m), s_n[tid]);
         __syncthreads();
         if (tid == 0) {
             bool any = false;
@@ -379,7 +408,7 @@ __global__ void __launch_bounds__(256) select_kernel(ClusterArgs a) {
     int bestL = 0;
     for (int L = 1; L < nlev; ++L)
         if (s_db[L] < s_db[bestL]) bestL = L;
-    const int8_t* lab = a.lev + (int64_t)bestL * Mtot + off;
+    const int8_t* lab = lev + (size_t)bestL * m;
     for (int p = tid; p < m; p += 256) a.labels[off + p] = lab[p];
     if (tid == 0) a.bin_K[b] = bestL + 2;
 }
@@ -575,18 +604,18 @@ extern "C" int32_t sctda_bin_cluster(sctda_ctx* ctx, int32_t G, const double* d_
     double* gram = (double*)sctda_ws(ctx, WS_CLUSTER2, (size_t)h_gram * 8);
     if (!gram) return SCTDA_ERR_NOMEM;
     const size_t M = (size_t)h_mtot;
-    const size_t aux_bytes = M * (4 + 8 + 4 + 4 + 8 * kMaxK + 8 + (kMaxK - 1)) + 256;
+    const size_t aux_bytes = M * (4 + 8 + 4 + 4 + 16 * kMaxK + 8) + 256;
     unsigned char* aux = (unsigned char*)sctda_ws(ctx, WS_CLUSTER3, aux_bytes);
     if (!aux) return SCTDA_ERR_NOMEM;
     ClusterArgs a;
     a.nbins = nbins; a.max_K = max_K; a.bin_off = d_bin_off; a.gram_off = gram_off; a.gram = gram;
     a.T = (double*)aux;
-    a.mst_w = a.T + M * kMaxK;
+    a.TK = a.T + M * kMaxK;
+    a.mst_w = a.TK + M * kMaxK;
     a.dist = a.mst_w + M;
     a.mst_parent = (int32_t*)(a.dist + M);
     a.mst_order = a.mst_parent + M;
     a.mst_seq = a.mst_order + M;
-    a.lev = (int8_t*)(a.mst_seq + M);
     a.labels = d_labels; a.bin_K = d_bin_K;
     double* db = d_bin_db;
     if (!db) {
@@ -599,11 +628,12 @@ extern "C" int32_t sctda_bin_cluster(sctda_ctx* ctx, int32_t G, const double* d_
     static bool attr_set = false;
     if (!attr_set) {
         SCTDA_CUDA(ctx, cudaFuncSetAttribute(prim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        SCTDA_CUDA(ctx, cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
         attr_set = true;
     }
     prim_kernel<<<nbins, 256, prim_smem, st>>>(a);
     SCTDA_LAUNCH_CHECK(ctx, "prim_kernel");
-    select_kernel<<<nbins, 256, 0, st>>>(a);
+    select_kernel<<<nbins, 256, (size_t)h_max * (kMaxK - 1) + 16, st>>>(a);
     SCTDA_LAUNCH_CHECK(ctx, "select_kernel");
     return SCTDA_OK;
 }

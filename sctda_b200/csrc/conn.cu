@@ -198,6 +198,7 @@ struct PermArgs {
     int32_t* ties;
     double* scores;
     float* pm;                    // [gridDim.x][V][32]
+    unsigned long long* counter;  // work queue head (zeroed before the launch)
 };
 
 // STAGE: 0 = permutation rows read from global memory (KIND decides how), 1 = the current row is
@@ -213,13 +214,25 @@ __global__ void __launch_bounds__(NW * 32) conn_perm_kernel(PermArgs a) {
     float* pm = a.pm + (size_t)blockIdx.x * a.V * kLanes;
     const double cor = (double)a.V / (double)(a.V - 1);          // ref:989
     int buf = 0;
-    if (STAGE == 2 && (int64_t)blockIdx.x < a.items) {            // prologue: first row of this CTA
-        const int r0 = (int)(blockIdx.x % a.nchunks) * kPermChunk;
+    // Work items are claimed from a global queue, one ahead: all CTAs stay within ~2*gridDim
+    // consecutive items, i.e. on one or two gene tiles, whatever their relative speed (a static
+    // stride lets CTAs drift apart over many tiles on long runs and the tiles fall out of L2).
+    __shared__ long long s_claim[2];
+    if (threadIdx.x == 0) {
+        s_claim[0] = (long long)atomicAdd(a.counter, 1ull);
+        s_claim[1] = (long long)atomicAdd(a.counter, 1ull);
+    }
+    __syncthreads();
+    int64_t item = s_claim[0], next_item = s_claim[1];
+    if (STAGE == 2 && item < a.items) {                           // prologue: first row of this CTA
+        const int r0 = (int)(item % a.nchunks) * kPermChunk;
         const int32_t* src = a.perm + (size_t)r0 * a.S;
         for (int i = threadIdx.x; i < a.S; i += NW * 32) cp_async_4(s_perm + i, src + i);
     }
 
-    for (int64_t item = blockIdx.x; item < a.items; item += gridDim.x) {
+    for (; item < a.items; item = next_item, next_item = s_claim[0]) {
+        __syncthreads();                                          // everybody has read s_claim[0]
+        if (threadIdx.x == 0) s_claim[0] = (long long)atomicAdd(a.counter, 1ull);   // visible after the next barrier
         const int tileIdx = (int)(item / a.nchunks);
         const int chunk = (int)(item % a.nchunks);
         const int g = tileIdx * kLanes + lane;
@@ -243,7 +256,7 @@ __global__ void __launch_bounds__(NW * 32) conn_perm_kernel(PermArgs a) {
                 cp_async_commit_wait_all();          // this thread's part of the current row has landed
                 __syncthreads();                     // ... and everybody else's
                 int rn = r + 1;                      // the row this CTA processes next, if any
-                if (rn >= r_end) rn = (item + gridDim.x < a.items) ? (int)((item + gridDim.x) % a.nchunks) * kPermChunk : -1;
+                if (rn >= r_end) rn = (next_item < a.items) ? (int)(next_item % a.nchunks) * kPermChunk : -1;
                 if (rn >= 0) {
                     const int32_t* src = a.perm + (size_t)rn * a.S;
                     int32_t* dst = s_perm + (size_t)(buf ^ 1) * a.S;
@@ -509,8 +522,10 @@ extern "C" int32_t sctda_conn_perm_test(sctda_ctx* ctx, const sctda_graph* gr, i
     double* ET = nullptr;
     rc = launch_et_prep(ctx, gr, G, d_Y, ldy, log2_mode, &ET, st);
     if (rc) return rc;
-    double* inv_q = (double*)sctda_ws(ctx, WS_MISC, (size_t)gr->V * sizeof(double));
+    double* inv_q = (double*)sctda_ws(ctx, WS_MISC, (size_t)gr->V * sizeof(double) + 64);
     if (!inv_q) return SCTDA_ERR_NOMEM;
+    unsigned long long* counter = (unsigned long long*)(inv_q + gr->V);
+    SCTDA_CUDA(ctx, cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
     inv_size_kernel<<<(gr->V + 255) / 256, 256, 0, st>>>(gr->d_node_off, gr->V, inv_q);
     SCTDA_LAUNCH_CHECK(ctx, "inv_size_kernel");
     constexpr int NW = 32;
@@ -523,7 +538,7 @@ extern "C" int32_t sctda_conn_perm_test(sctda_ctx* ctx, const sctda_graph* gr, i
     a.adj_off = gr->d_adj_off; a.adj_idx = gr->d_adj_idx; a.adj_w = gr->d_adj_w;
     a.ET = ET; a.inv_q = inv_q; a.perm = d_perm; a.perm_gene_stride = perm_gene_stride;
     a.observed = d_observed; a.tie_rel = tie_rel > 0.0 ? tie_rel : 1e-9;
-    a.exceed = d_exceed; a.ties = d_ties; a.scores = d_scores;
+    a.exceed = d_exceed; a.ties = d_ties; a.scores = d_scores; a.counter = counter;
     int64_t grid64 = (int64_t)ctx->sm_count;          // one 1024-thread CTA per SM: the node-value scratch stays in L2
     if (grid64 > a.items) grid64 = a.items;
     const int grid = (int)grid64;

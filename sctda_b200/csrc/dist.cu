@@ -61,12 +61,13 @@ struct GemmArgs {
     int nprob;
     const int32_t* bin_off;      // [nprob+1] member offsets
     const int32_t* members;      // [Mtot]
-    const int64_t* tile_prefix;  // [nprob+1] number of 128x128 tiles before problem p
+    const int64_t* tile_prefix;  // [nprob+1] number of upper-triangular 128x128 tiles before problem p
     const int64_t* gram_off;     // [nprob+1] element offset of problem p's m x m output
     double* gram;
 };
 
-__device__ __forceinline__ void gemm_tile(const GemmArgs& a, const GemmProblem& pr, int ti, int tj, double* smem) {
+__device__ __forceinline__ void gemm_tile(const GemmArgs& a, const GemmProblem& pr, int ti, int tj, double* smem,
+                                          bool mirror) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp & 3, wn = warp >> 2;                 // 4 x 2 warps, warp tile 32 x 64
     const int m0 = ti * BM, n0 = tj * BN;
@@ -154,6 +155,7 @@ __device__ __forceinline__ void gemm_tile(const GemmArgs& a, const GemmProblem& 
                     if (gr == gc) v = 0.0;
                 }
                 pr.out[(int64_t)r * pr.ldo + c] = v;
+                if (mirror) pr.out[(int64_t)c * pr.ldo + r] = v;     // G is symmetric bit for bit (products commute)
             }
         }
     }
@@ -164,7 +166,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(GemmArgs a) {
     if (a.nprob == 0) {
         const int tn = (a.single.nb + BN - 1) / BN;
         const int64_t total = (int64_t)((a.single.na + BM - 1) / BM) * tn;
-        for (int64_t t = blockIdx.x; t < total; t += gridDim.x) gemm_tile(a, a.single, (int)(t / tn), (int)(t % tn), smem);
+        for (int64_t t = blockIdx.x; t < total; t += gridDim.x)
+            gemm_tile(a, a.single, (int)(t / tn), (int)(t % tn), smem, false);
         return;
     }
     const int64_t total = a.tile_prefix[a.nprob];
@@ -176,14 +179,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(GemmArgs a) {
         }
         const int m = a.bin_off[lo + 1] - a.bin_off[lo];
         const int tn = (m + BN - 1) / BN;
-        const int64_t lt = t - a.tile_prefix[lo];
+        int64_t lt = t - a.tile_prefix[lo];                  // index into the upper triangle of tiles, row-major
+        int ti = 0;
+        while (lt >= tn - ti) { lt -= tn - ti; ++ti; }
+        const int tj = ti + (int)lt;
         GemmProblem pr;
         pr.rows_a = pr.rows_b = a.members + a.bin_off[lo];
         pr.row0_a = pr.row0_b = 0;
         pr.na = pr.nb = m;
         pr.out = a.gram + a.gram_off[lo];
         pr.ldo = m;
-        gemm_tile(a, pr, (int)(lt / tn), (int)(lt % tn), smem);
+        gemm_tile(a, pr, ti, tj, smem, ti != tj);
     }
 }
 
