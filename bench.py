@@ -217,34 +217,55 @@ def fp64_probe_tflops(dev):
     return best
 
 
-def run_mapper(a, ctx, dev, steps, warmup):
+def run_mapper(a, ctx, dev, steps, warmup, rank=0, world=1):
+    """world == 1: BASELINE.json configs[1] (20k x 5k, correlation, r=30, gain 3) on one GPU.
+    world > 1: configs[2] (100k cells x 2k genes, euclidean), per-patch clustering sharded over the
+    ranks by descending m^2, labels exchanged by one all_gather (NCCL), the rest replicated."""
     import torch
+    import torch.distributed as dist
     from sctda_b200 import mapper, synth
-    N, G, r, gain = a.mapper_cells, a.mapper_genes, a.mapper_resolution, a.mapper_gain
+    if world > 1:
+        N, G, metric = 100000, 2000, 'euclidean'
+    else:
+        N, G, metric = a.mapper_cells, a.mapper_genes, a.mapper_metric
+    r, gain = a.mapper_resolution, a.mapper_gain
     X = synth.expression_genes_torch(G, N, seed=synth.SEED + 11, device=dev).T.contiguous()      # cells x genes
     t0 = time.perf_counter()
     lens = mapper.pca_lens_device(X)
+    if world > 1:
+        dist.broadcast(lens, src=0)                         # every rank must cut the same cover
     torch.cuda.synchronize()
     lens_ms = 1e3 * (time.perf_counter() - t0)
+
+    def build(prof):
+        if world > 1:
+            return mapper.build_graph_distributed(ctx, X, lens, r, gain, metric=metric, profile=prof)
+        return mapper.build_graph_device(ctx, X, lens, r, gain, metric=metric, profile=prof)
     prof = {}
     for _ in range(max(1, warmup)):
-        mapper.build_graph_device(ctx, X, lens, r, gain, metric=a.mapper_metric, profile=prof)
+        build(prof)
     times, gemm = [], []
     for _ in range(steps):
         prof = {}
-        res = mapper.build_graph_device(ctx, X, lens, r, gain, metric=a.mapper_metric, profile=prof)
-        times.append(prof['total_ms'])
+        if world > 1:
+            dist.barrier()
+        res = build(prof)
+        t = torch.tensor([prof['total_ms']], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        times.append(float(t.item()))
         gemm.append(prof['gemm_ms'])
     bin_off = res.bin_off.cpu().numpy().astype(numpy.int64)
     m = bin_off[1:] - bin_off[:-1]
     sum_m2 = float((m * m).sum())
-    flops = 2.0 * G * sum_m2                                   # intra-patch tiles, no symmetry credit
+    flops = 2.0 * G * sum_m2 / world                          # this rank's share (LPT balances m^2)
     ms = float(numpy.mean(times))
     gms = float(numpy.mean(gemm))
     peak = fp64_probe_tflops(dev)
-    out = {'metric': 'Mapper build cells/s', 'value': N / (ms * 1e-3), 'unit': 'cells/s', 'ms_per_build': ms,
+    out = {'metric': 'Mapper build cells/s', 'value': N / (ms * 1e-3), 'unit': 'cells/s', 'ms_per_build': ms, 'n_gpus': world,
            'config': {'workload': 'Mapper build: %d cells x %d genes, %s metric, PCA lens, resolution %d, gain %g, '
-                                  'max_K 5, 1 B200' % (N, G, a.mapper_metric, r, gain),
+                                  'max_K 5, %d B200%s' % (N, G, metric, r, gain, world,
+                                                          ', patches sharded by descending m^2' if world > 1 else ''),
                       'cover_multiplicity': float(prof['Mtot']) / N, 'nodes': prof['V'], 'edges': prof['E'],
                       'largest_patch': int(m.max()), 'sum_m2': sum_m2},
            'stages_ms': {k[:-3]: round(float(v), 3) for k, v in prof.items()
@@ -253,6 +274,9 @@ def run_mapper(a, ctx, dev, steps, warmup):
            'roofline': {'bound': 'tensor', 'achieved': flops / (gms * 1e-3) / 1e12, 'peak': peak, 'unit': 'TFLOP/s',
                         'frac': flops / (gms * 1e-3) / 1e12 / peak, 'traffic': None, 'kernel': 'gemm_kernel (FP64 DMMA)',
                         'kernel_ms': gms, 'flops': flops,
+                        'executed_flops': 'upper-triangular 128x128 tiles only (the Gram tile is symmetric bit for bit): '
+                                          'about half of `flops`, which is SURVEY.md 8d\'s algorithmic 2*G*sum m_b^2 '
+                                          'without symmetry credit, so frac can exceed 1',
                         'peak_source': 'torch.matmul float64 6144^3 (cuBLAS DGEMM) probe in this run'}}
     del X
     torch.cuda.empty_cache()
@@ -386,14 +410,14 @@ def run_own(a):
                     'the binding resource is the L2->SM gather of 8*Mtot bytes per gene*perm (DESIGN.md)'}
 
     mapper_line = None
-    if rank == 0 and not a.no_mapper:
+    if not a.no_mapper:
         if not a.no_e2e:
             del Yh, Ph
         else:
             del Y, perms
         torch.cuda.empty_cache()
-        mapper_line = run_mapper(a, ctx, dev, max(1, min(a.steps, 3)), 2)
-        if world == 1 and not a.no_cpu:
+        mapper_line = run_mapper(a, ctx, dev, max(1, min(a.steps, 3)), 2, rank, world)
+        if rank == 0 and world == 1 and not a.no_cpu:
             mapper_line['cpu_baseline'] = mapper_cpu_sample()
     if rank == 0:
         cpu = None

@@ -63,7 +63,8 @@ int64_t sctda_launch_count(const sctda_ctx* ctx);
 /* Measurement aid (bench.py "roofline"): when enabled, every hot-path call brackets its
  * DOMINANT kernel (conn_perm_kernel for sctda_conn_perm_test) with CUDA events on the
  * caller's stream.  sctda_last_kernel_ms waits for that kernel to finish (host sync on
- * the event) and returns its duration in milliseconds. */
+ * the event) and returns its duration in milliseconds, summed over the launches of the last
+ * call (sctda_bin_cluster launches the contraction once per batch of patches). */
 int32_t sctda_set_kernel_timing(sctda_ctx* ctx, int32_t enabled);
 int32_t sctda_last_kernel_ms(sctda_ctx* ctx, float* out_ms);
 
@@ -201,7 +202,8 @@ int32_t sctda_cover_fill(sctda_ctx* ctx, int32_t N, int32_t r, const int32_t* d_
  * (stat 0 = 'db'), K_max = 2 if m <= 5 else min(m/2, max_K); a one-cell patch is one node.
  * d_labels [total] cluster of each membership (numbered by smallest member), d_bin_K [nbins],
  * d_bin_db [nbins, 8] the index of K = 2, 3, ... (NaN where not evaluated; may be NULL).
- * Synchronises the host once (workspace sizing).  max_K <= 8, patches of <= 10,000 cells. */
+ * Synchronises the host once (patch sizes: batching of the Gram tiles to the free memory,
+ * largest patches first).  max_K <= 8. */
 int32_t sctda_bin_cluster(sctda_ctx* ctx, int32_t G, const double* d_Xn, int64_t ldxn, int32_t nbins,
                           const int32_t* d_bin_off, const int32_t* d_members, int32_t max_K, int32_t stat,
                           int32_t* d_labels, int32_t* d_bin_K, double* d_bin_db, void* stream);

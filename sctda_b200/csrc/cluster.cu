@@ -20,11 +20,14 @@
 //     with popc prefix sums into the lexicographically sorted edge list.
 #include <math.h>
 
+#include <algorithm>
+#include <vector>
+
 #include "common.cuh"
 
-int sctda_internal_gram_bins(sctda_ctx* ctx, int G, const double* d_Xn, int64_t ldxn, int nbins,
-                             const int32_t* d_bin_off, const int32_t* d_members, const int64_t* d_tile_prefix,
-                             const int64_t* d_gram_off, double* d_gram, cudaStream_t st);
+int sctda_internal_gram_bins(sctda_ctx* ctx, int G, const double* d_Xn, int64_t ldxn, int nprob,
+                             const int32_t* d_prob_bin, const int32_t* d_bin_off, const int32_t* d_members,
+                             const int64_t* d_tile_prefix, const int64_t* d_gram_off, double* d_gram, cudaStream_t st);
 
 namespace {
 
@@ -65,11 +68,6 @@ __global__ void __launch_bounds__(1024) scan_kernel(const int32_t* __restrict__ 
     __syncthreads();
     long long run = s_sum[t];
     for (int64_t i = lo; i < hi; ++i) { out[i] = (TOut)run; run += f(in[i]); }
-}
-
-__global__ void bin_size_kernel(int n, const int32_t* __restrict__ off, int32_t* __restrict__ c) {
-    int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b < n) c[b] = off[b + 1] - off[b];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -122,8 +120,15 @@ __global__ void __launch_bounds__(256) cover_scan_kernel(const unsigned long lon
 struct ClusterArgs {
     int nbins, max_K;
     const int32_t* bin_off;
-    const int64_t* gram_off;
+    const int32_t* prob_bin;  // [nprob] patch index of problem p of the current batch (largest first)
+    int prob0;                // first problem served by this launch
+    const int64_t* gram_off;  // [nprob+1] element offset of problem p's Gram tile in `gram`
     const double* gram;
+    int prim_cap, lev_cap;    // largest m whose Prim state / level labels fit in shared memory
+    double* pkey;             // [Mtot] global fallbacks for patches above the caps
+    double* pgpp;
+    int32_t* ppar;
+    int8_t* lev_g;            // [Mtot][kMaxK-1]
     int32_t* mst_parent;      // [Mtot] parent of local vertex u in the tree (-1 for the root)
     double* mst_w;            // [Mtot] weight of that edge
     int32_t* mst_order;       // [Mtot] insertion step of vertex u (-1 for the root)
@@ -145,14 +150,16 @@ __global__ void __launch_bounds__(256) prim_kernel(ClusterArgs a) {
     __shared__ double s_rk[8];
     __shared__ int s_ri[8];
     __shared__ int s_u;
-    const int b = blockIdx.x;
+    const int prob = a.prob0 + blockIdx.x;
+    const int b = a.prob_bin[prob];
     const int off = a.bin_off[b], m = a.bin_off[b + 1] - off;
     if (m == 0) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    double* key = (double*)s_raw;                 // >= 0: best known distance to the tree; -1: in the tree
-    double* gpp = key + m;
-    int* par = (int*)(gpp + m);
-    const double* Gm = a.gram + a.gram_off[b];
+    const bool big = m > a.prim_cap;
+    double* key = big ? a.pkey + off : (double*)s_raw;   // >= 0: best known distance to the tree; -1: in the tree
+    double* gpp = big ? a.pgpp + off : key + m;
+    int* par = big ? a.ppar + off : (int*)(gpp + m);
+    const double* Gm = a.gram + a.gram_off[prob];
     for (int q = tid; q < m; q += 256) {
         key[q] = INFINITY;
         gpp[q] = Gm[(int64_t)q * m + q];
@@ -201,6 +208,79 @@ __global__ void __launch_bounds__(256) prim_kernel(ClusterArgs a) {
     }
 }
 
+// Prim with the keys in REGISTERS: 512 threads, thread t owns vertices t, t+512, ... (KPT of them);
+// |row|^2 and the parents live in shared memory.  One barrier per step (double-buffered warp
+// results); the only serial latency left is the fetch of the next row of the Gram tile.
+template <int KPT>
+__global__ void __launch_bounds__(512) prim_reg_kernel(ClusterArgs a) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    __shared__ double s_rk[2][16];
+    __shared__ int s_ri[2][16];
+    const int prob = a.prob0 + blockIdx.x;
+    const int b = a.prob_bin[prob];
+    const int off = a.bin_off[b], m = a.bin_off[b + 1] - off;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double* gpp = (double*)s_raw;
+    int* par = (int*)(gpp + m);
+    const double* Gm = a.gram + a.gram_off[prob];
+    double key[KPT];
+#pragma unroll
+    for (int i = 0; i < KPT; ++i) {
+        const int q = tid + 512 * i;
+        key[i] = (q < m && q != 0) ? INFINITY : -1.0;          // -1: in the tree (or not a vertex)
+        if (q < m) { gpp[q] = Gm[(int64_t)q * m + q]; par[q] = -1; }
+    }
+    if (tid == 0) { a.mst_parent[off] = -1; a.mst_w[off] = 0.0; a.mst_order[off] = -1; a.mst_seq[off] = 0; }
+    __syncthreads();
+    int u = 0;
+    for (int t = 0; t < m - 1; ++t) {
+        const double gu = gpp[u];
+        const double* row = Gm + (int64_t)u * m;
+        double g[KPT];
+#pragma unroll
+        for (int i = 0; i < KPT; ++i) g[i] = key[i] >= 0.0 ? row[tid + 512 * i] : 0.0;
+        double bk = INFINITY;
+        int bi = 0x7fffffff;
+#pragma unroll
+        for (int i = 0; i < KPT; ++i) {
+            const int q = tid + 512 * i;
+            double k = key[i];
+            if (k >= 0.0) {
+                const double d = dist2(gu, gpp[q], g[i]);
+                if (d < k) { k = d; key[i] = d; par[q] = u; }
+                if (k < bk || (k == bk && q < bi)) { bk = k; bi = q; }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ok = __shfl_xor_sync(0xffffffffu, bk, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ok < bk || (ok == bk && oi < bi)) { bk = ok; bi = oi; }
+        }
+        const int pp = t & 1;
+        if (lane == 0) { s_rk[pp][warp] = bk; s_ri[pp][warp] = bi; }
+        __syncthreads();
+        bk = s_rk[pp][0];
+        bi = s_ri[pp][0];
+#pragma unroll
+        for (int w = 1; w < 16; ++w) {
+            const double ok = s_rk[pp][w];
+            const int oi = s_ri[pp][w];
+            if (ok < bk || (ok == bk && oi < bi)) { bk = ok; bi = oi; }
+        }
+        u = bi;
+        const int sel = (u & 511) == tid ? (u >> 9) : -1;
+#pragma unroll
+        for (int i = 0; i < KPT; ++i) key[i] = (sel == i) ? -1.0 : key[i];     // stays in registers
+        if (sel >= 0) {
+            a.mst_parent[off + u] = par[u];
+            a.mst_w[off + u] = bk;
+            a.mst_order[off + u] = t;
+            a.mst_seq[off + t + 1] = u;
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // cut + Davies-Bouldin model selection per patch
 // ---------------------------------------------------------------------------------------------
@@ -221,10 +301,12 @@ __device__ __forceinline__ double masked_seq_sum(const double* __restrict__ v, i
     return acc;
 }
 
-__global__ void __launch_bounds__(256) select_kernel(ClusterArgs a) {
+constexpr int kSelThreads = 1024;
+
+__global__ void __launch_bounds__(kSelThreads) select_kernel(ClusterArgs a) {
     extern __shared__ __align__(16) unsigned char s_dyn[];      // labels of every level: int8 [nlev][m]
-    __shared__ double s_rk[8];
-    __shared__ int s_ri[8], s_ro[8];
+    __shared__ double s_rk[32];
+    __shared__ int s_ri[32], s_ro[32];
     __shared__ int s_heavy[kMaxK];               // vertices whose edge is the h-th heaviest
     __shared__ int s_cof[kMaxK];                 // fine cluster -> coarse cluster of the level under evaluation
     __shared__ int s_fine_rep[kMaxK];
@@ -232,25 +314,24 @@ __global__ void __launch_bounds__(256) select_kernel(ClusterArgs a) {
     __shared__ double s_cc[kMaxK][kMaxK];
     __shared__ double s_S[kMaxK];
     __shared__ double s_db[kMaxK];
-    const int b = blockIdx.x;
+    const int prob = a.prob0 + blockIdx.x;
+    const int b = a.prob_bin[prob];
     const int off = a.bin_off[b], m = a.bin_off[b + 1] - off;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid < kMaxK) a.bin_db[(int64_t)b * kMaxK + tid] = NAN;
-    if (m == 0) { if (tid == 0) a.bin_K[b] = 0; return; }
-    if (m == 1) { if (tid == 0) { a.bin_K[b] = 1; a.labels[off] = 0; } return; }
-    const double* Gm = a.gram + a.gram_off[b];
+    if (m < 2) return;                           // handled by trivial_bins_kernel
+    const double* Gm = a.gram + a.gram_off[prob];
     const int kmax = m <= 5 ? 2 : min(m / 2, a.max_K);
     const int nlev = kmax - 1;                   // level L (0-based) = L+1 edges removed = L+2 clusters
     const double* w = a.mst_w + off;
     const int32_t* ord = a.mst_order + off;
     const int32_t* par = a.mst_parent + off;
     const int32_t* seq = a.mst_seq + off;
-    int8_t* lev = (int8_t*)s_dyn;
+    int8_t* lev = m > a.lev_cap ? a.lev_g + (size_t)off * (kMaxK - 1) : (int8_t*)s_dyn;
     // (c) the nlev heaviest tree edges: (weight desc, insertion order desc)
     for (int h = 0; h < nlev; ++h) {
         double bk = -1.0;
         int bo = -1, bi = -1;
-        for (int q = tid; q < m; q += 256) {
+        for (int q = tid; q < m; q += kSelThreads) {
             int o = ord[q];
             if (o < 0) continue;
             bool taken = false;
@@ -269,7 +350,7 @@ __global__ void __launch_bounds__(256) select_kernel(ClusterArgs a) {
         if (lane == 0) { s_rk[warp] = bk; s_ro[warp] = bo; s_ri[warp] = bi; }
         __syncthreads();
         if (tid == 0) {
-            for (int x = 1; x < 8; ++x)
+            for (int x = 1; x < kSelThreads / 32; ++x)
                 if (s_rk[x] > bk || (s_rk[x] == bk && s_ro[x] > bo)) { bk = s_rk[x]; bo = s_ro[x]; bi = s_ri[x]; }
             s_heavy[h] = bi;
         }
@@ -311,17 +392,17 @@ __global__ void __launch_bounds__(256) select_kernel(ClusterArgs a) {
     double* TK = a.TK + (int64_t)off * kMaxK;                  // [m][kMaxK], per level
     double* dist = a.dist + off;
     // (e) T[p][f] = sum over q ascending of G[q][p] for q in fine cluster f
-    for (int p = tid; p < m; p += 256) {
+    for (int p = tid; p < m; p += kSelThreads) {
         double acc[kMaxK];
 #pragma unroll
         for (int f = 0; f < kMaxK; ++f) acc[f] = 0.0;
         int q = 0;
-        for (; q + 4 <= m; q += 4) {
-            double g[4];
+        for (; q + 8 <= m; q += 8) {
+            double g[8];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) g[u] = Gm[(int64_t)(q + u) * m + p];
+            for (int u = 0; u < 8; ++u) g[u] = Gm[(int64_t)(q + u) * m + p];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < 8; ++u) {
                 const int fq = fine[q + u];                    // uniform across the CTA
 #pragma unroll
                 for (int f = 0; f < kMaxK; ++f)
@@ -345,7 +426,7 @@ __global__ void __launch_bounds__(256) select_kernel(ClusterArgs a) {
         const int8_t* lab = lev + (size_t)L * m;
         if (tid < F) s_cof[tid] = lab[s_fine_rep[tid]];
         __syncthreads();
-        for (int p = tid; p < m; p += 256) {                    // TK[p][J] = sum_{f in J, ascending} T[p][f]
+        for (int p = tid; p < m; p += kSelThreads) {                    // TK[p][J] = sum_{f in J, ascending} T[p][f]
             double tk[kMaxK];
 #pragma unroll
             for (int J = 0; J < kMaxK; ++J) tk[J] = 0.0;
@@ -371,7 +452,7 @@ __global__ void __launch_bounds__(256) select_kernel(ClusterArgs a) {
             s_cc[I][J] = __ddiv_rn(acc, __dmul_rn(s_n[I], s_n[J]));
         }
         __syncthreads();
-        for (int p = tid; p < m; p += 256) {                    // |x_p - c_I|
+        for (int p = tid; p < m; p += kSelThreads) {                    // |x_p - c_I|
             const int I = lab[p];
             const double xc = __ddiv_rn(TK[(int64_t)p * kMaxK + I], s_n[I]);
             const double d2 = fmax(__dadd_rn(fma(-2.0, xc, Gm[(int64_t)p * m + p]), s_cc[I][I]), 0.0);
@@ -409,8 +490,19 @@ __global__ void __launch_bounds__(256) select_kernel(ClusterArgs a) {
     for (int L = 1; L < nlev; ++L)
         if (s_db[L] < s_db[bestL]) bestL = L;
     const int8_t* lab = lev + (size_t)bestL * m;
-    for (int p = tid; p < m; p += 256) a.labels[off + p] = lab[p];
+    for (int p = tid; p < m; p += kSelThreads) a.labels[off + p] = lab[p];
     if (tid == 0) a.bin_K[b] = bestL + 2;
+}
+
+// patches with 0 or 1 cells, and the NaN fill of the score table
+__global__ void trivial_bins_kernel(int nbins, const int32_t* __restrict__ bin_off, int32_t* __restrict__ labels,
+                                    int32_t* __restrict__ bin_K, double* __restrict__ bin_db) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nbins) return;
+    for (int i = 0; i < kMaxK; ++i) bin_db[(int64_t)b * kMaxK + i] = NAN;
+    const int m = bin_off[b + 1] - bin_off[b];
+    if (m == 0) bin_K[b] = 0;
+    if (m == 1) { bin_K[b] = 1; labels[bin_off[b]] = 0; }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -566,6 +658,7 @@ extern "C" int32_t sctda_bin_cluster(sctda_ctx* ctx, int32_t G, const double* d_
                                      const int32_t* d_bin_off, const int32_t* d_members, int32_t max_K, int32_t stat,
                                      int32_t* d_labels, int32_t* d_bin_K, double* d_bin_db, void* stream) {
     if (!ctx) return SCTDA_ERR_INVALID;
+    SCTDA_TIME_RESET(ctx);
     if (G < 1 || nbins < 0 || !d_Xn || ldxn < G || !d_bin_off || !d_members || !d_labels || !d_bin_K)
         return sctda_fail(ctx, SCTDA_ERR_INVALID, "bin_cluster: bad arguments%s");
     if (max_K < 2 || max_K > kMaxK) return sctda_fail(ctx, SCTDA_ERR_UNSUPPORTED, "bin_cluster: max_K must be in 2..8%s");
@@ -575,66 +668,150 @@ extern "C" int32_t sctda_bin_cluster(sctda_ctx* ctx, int32_t G, const double* d_
     if (nbins == 0) return SCTDA_OK;
     cudaStream_t st = (cudaStream_t)stream;
     SCTDA_CUDA(ctx, cudaSetDevice(ctx->device));
-    // sizes: tile prefix, Gram offsets, largest patch  (one small host sync to size the workspace)
-    int64_t* pre = (int64_t*)sctda_ws(ctx, WS_CLUSTER, (size_t)(nbins + 1) * 16 + 64);
-    if (!pre) return SCTDA_ERR_NOMEM;
-    int64_t* tile_prefix = pre;
-    int64_t* gram_off = pre + (nbins + 1);
-    int32_t* d_max = (int32_t*)(gram_off + (nbins + 1));
-    // bin sizes as an array: reuse d_bin_K as scratch for the counts
-    bin_size_kernel<<<(nbins + 255) / 256, 256, 0, st>>>(nbins, d_bin_off, d_bin_K);
-    SCTDA_LAUNCH_CHECK(ctx, "bin_size_kernel");
-    scan_kernel<int64_t><<<1, 1024, 0, st>>>(d_bin_K, nbins, MAP_TILES, tile_prefix, d_max);
-    SCTDA_LAUNCH_CHECK(ctx, "scan_kernel<tiles>");
-    scan_kernel<int64_t><<<1, 1024, 0, st>>>(d_bin_K, nbins, MAP_SQUARE, gram_off, nullptr);
-    SCTDA_LAUNCH_CHECK(ctx, "scan_kernel<square>");
-    int64_t h_gram = 0;
-    int32_t h_max = 0, h_mtot = 0;
-    SCTDA_CUDA(ctx, cudaMemcpyAsync(&h_gram, gram_off + nbins, 8, cudaMemcpyDeviceToHost, st));
-    SCTDA_CUDA(ctx, cudaMemcpyAsync(&h_max, d_max, 4, cudaMemcpyDeviceToHost, st));
-    SCTDA_CUDA(ctx, cudaMemcpyAsync(&h_mtot, d_bin_off + nbins, 4, cudaMemcpyDeviceToHost, st));
+    // patch sizes on the host (one small synchronising copy): batches, launch order, workspace sizes
+    std::vector<int32_t> h_off((size_t)nbins + 1);
+    SCTDA_CUDA(ctx, cudaMemcpyAsync(h_off.data(), d_bin_off, ((size_t)nbins + 1) * 4, cudaMemcpyDeviceToHost, st));
     SCTDA_CUDA(ctx, cudaStreamSynchronize(st));
-    if (h_mtot == 0) {
-        SCTDA_CUDA(ctx, cudaMemsetAsync(d_bin_K, 0, (size_t)nbins * 4, st));
-        return SCTDA_OK;
-    }
-    const size_t prim_smem = (size_t)h_max * 20 + 16;
-    if (prim_smem > 200 * 1024)
-        return sctda_fail(ctx, SCTDA_ERR_UNSUPPORTED, "bin_cluster: a patch with more than 10,000 cells is not served%s");
-    double* gram = (double*)sctda_ws(ctx, WS_CLUSTER2, (size_t)h_gram * 8);
-    if (!gram) return SCTDA_ERR_NOMEM;
-    const size_t M = (size_t)h_mtot;
-    const size_t aux_bytes = M * (4 + 8 + 4 + 4 + 16 * kMaxK + 8) + 256;
-    unsigned char* aux = (unsigned char*)sctda_ws(ctx, WS_CLUSTER3, aux_bytes);
-    if (!aux) return SCTDA_ERR_NOMEM;
-    ClusterArgs a;
-    a.nbins = nbins; a.max_K = max_K; a.bin_off = d_bin_off; a.gram_off = gram_off; a.gram = gram;
-    a.T = (double*)aux;
-    a.TK = a.T + M * kMaxK;
-    a.mst_w = a.TK + M * kMaxK;
-    a.dist = a.mst_w + M;
-    a.mst_parent = (int32_t*)(a.dist + M);
-    a.mst_order = a.mst_parent + M;
-    a.mst_seq = a.mst_order + M;
-    a.labels = d_labels; a.bin_K = d_bin_K;
+    const size_t M = (size_t)h_off[nbins];
     double* db = d_bin_db;
     if (!db) {
         db = (double*)sctda_ws(ctx, WS_MISC, (size_t)nbins * kMaxK * 8);
         if (!db) return SCTDA_ERR_NOMEM;
     }
-    a.bin_db = db;
-    int rc = sctda_internal_gram_bins(ctx, G, d_Xn, ldxn, nbins, d_bin_off, d_members, tile_prefix, gram_off, gram, st);
-    if (rc) return rc;
+    trivial_bins_kernel<<<(nbins + 255) / 256, 256, 0, st>>>(nbins, d_bin_off, d_labels, d_bin_K, db);
+    SCTDA_LAUNCH_CHECK(ctx, "trivial_bins_kernel");
+    std::vector<int32_t> order;
+    for (int b = 0; b < nbins; ++b)
+        if (h_off[b + 1] - h_off[b] >= 2) order.push_back(b);
+    if (order.empty()) return SCTDA_OK;
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
+        return (h_off[x + 1] - h_off[x]) > (h_off[y + 1] - h_off[y]);          // largest patches first
+    });
+    // Gram workspace: patches are processed in batches whose tiles fit in one of TWO buffers, so
+    // that the contraction of batch i+1 (caller's stream) overlaps the MST / selection kernels of
+    // batch i (the context's auxiliary stream): the few largest patches bound the MST time of a
+    // batch and would otherwise leave most SMs idle.
+    size_t free_b = 0, total_b = 0;
+    SCTDA_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
+    free_b += ctx->slot_bytes[WS_CLUSTER2] + ctx->slot_bytes[WS_CLUSTER4];
+    size_t budget = free_b / 4;
+    if (budget > ((size_t)16 << 30)) budget = (size_t)16 << 30;
+    if (budget < ((size_t)256 << 20)) budget = (size_t)256 << 20;
+    const size_t aux_bytes = M * (8 * (2 * kMaxK + 4) + 4 * 4 + (kMaxK - 1)) + 256;
+    unsigned char* aux = (unsigned char*)sctda_ws(ctx, WS_CLUSTER3, aux_bytes);
+    if (!aux) return SCTDA_ERR_NOMEM;
+    ClusterArgs a;
+    a.nbins = nbins; a.max_K = max_K; a.bin_off = d_bin_off;
+    a.T = (double*)aux;
+    a.TK = a.T + M * kMaxK;
+    a.mst_w = a.TK + M * kMaxK;
+    a.dist = a.mst_w + M;
+    a.pkey = a.dist + M;
+    a.pgpp = a.pkey + M;
+    a.mst_parent = (int32_t*)(a.pgpp + M);
+    a.mst_order = a.mst_parent + M;
+    a.mst_seq = a.mst_order + M;
+    a.ppar = a.mst_seq + M;
+    a.lev_g = (int8_t*)(a.ppar + M);
+    a.labels = d_labels; a.bin_K = d_bin_K; a.bin_db = db;
+    a.prim_cap = 0;                               // the generic kernel keeps its state in global memory
+    a.lev_cap = (80 * 1024 - 16) / (kMaxK - 1);
     static bool attr_set = false;
     if (!attr_set) {
-        SCTDA_CUDA(ctx, cudaFuncSetAttribute(prim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        SCTDA_CUDA(ctx, cudaFuncSetAttribute(prim_reg_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        SCTDA_CUDA(ctx, cudaFuncSetAttribute(prim_reg_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         SCTDA_CUDA(ctx, cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
         attr_set = true;
     }
-    prim_kernel<<<nbins, 256, prim_smem, st>>>(a);
-    SCTDA_LAUNCH_CHECK(ctx, "prim_kernel");
-    select_kernel<<<nbins, 256, (size_t)h_max * (kMaxK - 1) + 16, st>>>(a);
-    SCTDA_LAUNCH_CHECK(ctx, "select_kernel");
+    if (!ctx->aux_stream) {
+        SCTDA_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 4; ++i) SCTDA_CUDA(ctx, cudaEventCreateWithFlags(&ctx->pipe_ev[i], cudaEventDisableTiming));
+    }
+    cudaStream_t aux_st = ctx->aux_stream;
+    // batches (host only)
+    struct Batch { size_t pos, end, elems; int max_lev; std::vector<int64_t> tiles, goff; };
+    std::vector<Batch> batches;
+    for (size_t pos = 0; pos < order.size();) {
+        Batch bt;
+        bt.pos = pos; bt.elems = 0; bt.max_lev = 0;
+        bt.tiles.assign(1, 0);
+        bt.goff.assign(1, 0);
+        size_t end = pos;
+        while (end < order.size()) {
+            const int64_t m = h_off[order[end] + 1] - h_off[order[end]];
+            if (end > pos && (bt.elems + (size_t)(m * m)) * 8 > budget) break;
+            bt.elems += (size_t)(m * m);
+            const int64_t q = (m + 127) / 128;
+            bt.tiles.push_back(bt.tiles.back() + q * (q + 1) / 2);            // upper-triangular 128x128 tiles
+            bt.goff.push_back((int64_t)bt.elems);
+            if (m <= a.lev_cap && m > bt.max_lev) bt.max_lev = (int)m;
+            ++end;
+        }
+        bt.end = end;
+        batches.push_back(std::move(bt));
+        pos = end;
+    }
+    // allocate both buffers up front (no reallocation while the pipeline runs)
+    size_t need0 = 0, need1 = 0, meta0 = 0, meta1 = 0;
+    for (size_t i = 0; i < batches.size(); ++i) {
+        const size_t nbb = batches[i].end - batches[i].pos;
+        const size_t mb = (nbb + 1) * 16 + nbb * 4 + 64;
+        if (i % 2 == 0) { need0 = std::max(need0, batches[i].elems * 8); meta0 = std::max(meta0, mb); }
+        else { need1 = std::max(need1, batches[i].elems * 8); meta1 = std::max(meta1, mb); }
+    }
+    double* gram_buf[2] = {(double*)sctda_ws(ctx, WS_CLUSTER2, need0), need1 ? (double*)sctda_ws(ctx, WS_CLUSTER4, need1) : nullptr};
+    unsigned char* meta_buf[2] = {(unsigned char*)sctda_ws(ctx, WS_CLUSTER, meta0),
+                                  meta1 ? (unsigned char*)sctda_ws(ctx, WS_CLUSTER5, meta1) : nullptr};
+    if (!gram_buf[0] || !meta_buf[0] || (need1 && (!gram_buf[1] || !meta_buf[1]))) return SCTDA_ERR_NOMEM;
+    for (size_t i = 0; i < batches.size(); ++i) {
+        const Batch& bt = batches[i];
+        const int k = (int)(i & 1);
+        const int nb = (int)(bt.end - bt.pos);
+        if (i >= 2) SCTDA_CUDA(ctx, cudaStreamWaitEvent(st, ctx->pipe_ev[2 + k], 0));   // buffer k is free again
+        int64_t* d_tiles = (int64_t*)meta_buf[k];
+        int64_t* d_goff = d_tiles + (nb + 1);
+        int32_t* d_prob = (int32_t*)(d_goff + (nb + 1));
+        SCTDA_CUDA(ctx, cudaMemcpyAsync(d_tiles, bt.tiles.data(), (size_t)(nb + 1) * 8, cudaMemcpyHostToDevice, st));
+        SCTDA_CUDA(ctx, cudaMemcpyAsync(d_goff, bt.goff.data(), (size_t)(nb + 1) * 8, cudaMemcpyHostToDevice, st));
+        SCTDA_CUDA(ctx, cudaMemcpyAsync(d_prob, order.data() + bt.pos, (size_t)nb * 4, cudaMemcpyHostToDevice, st));
+        a.prob_bin = d_prob; a.gram_off = d_goff; a.gram = gram_buf[k];
+        int rc = sctda_internal_gram_bins(ctx, G, d_Xn, ldxn, nb, d_prob, d_bin_off, d_members, d_tiles, d_goff, gram_buf[k], st);
+        if (rc) return rc;
+        SCTDA_CUDA(ctx, cudaEventRecord(ctx->pipe_ev[k], st));
+        SCTDA_CUDA(ctx, cudaStreamWaitEvent(aux_st, ctx->pipe_ev[k], 0));
+        // MST: patches are sorted by size; [0,n_huge) above 16,384 cells (generic kernel, state in
+        // global memory), [n_huge,n_mid) above 4,096 (32 register keys per thread), the rest 8
+        int n_huge = 0, n_mid = 0;
+        for (size_t j = bt.pos; j < bt.end; ++j) {
+            const int m = h_off[order[j] + 1] - h_off[order[j]];
+            if (m > 16384) ++n_huge;
+            if (m > 4096) ++n_mid;
+        }
+        if (n_huge) {
+            a.prob0 = 0;
+            prim_kernel<<<n_huge, 256, 16, aux_st>>>(a);
+            SCTDA_LAUNCH_CHECK(ctx, "prim_kernel");
+        }
+        if (n_mid > n_huge) {
+            a.prob0 = n_huge;
+            const int mm = h_off[order[bt.pos + n_huge] + 1] - h_off[order[bt.pos + n_huge]];
+            prim_reg_kernel<32><<<n_mid - n_huge, 512, (size_t)mm * 12 + 16, aux_st>>>(a);
+            SCTDA_LAUNCH_CHECK(ctx, "prim_reg_kernel<32>");
+        }
+        if (nb > n_mid) {
+            a.prob0 = n_mid;
+            const int mm = h_off[order[bt.pos + n_mid] + 1] - h_off[order[bt.pos + n_mid]];
+            prim_reg_kernel<8><<<nb - n_mid, 512, (size_t)mm * 12 + 16, aux_st>>>(a);
+            SCTDA_LAUNCH_CHECK(ctx, "prim_reg_kernel<8>");
+        }
+        a.prob0 = 0;
+        select_kernel<<<nb, kSelThreads, (size_t)bt.max_lev * (kMaxK - 1) + 16, aux_st>>>(a);
+        SCTDA_LAUNCH_CHECK(ctx, "select_kernel");
+        SCTDA_CUDA(ctx, cudaEventRecord(ctx->pipe_ev[2 + k], aux_st));
+    }
+    // the caller's stream continues only after every batch is done
+    SCTDA_CUDA(ctx, cudaStreamWaitEvent(st, ctx->pipe_ev[2], 0));
+    if (batches.size() > 1) SCTDA_CUDA(ctx, cudaStreamWaitEvent(st, ctx->pipe_ev[3], 0));
     return SCTDA_OK;
 }
 

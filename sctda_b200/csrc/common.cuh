@@ -18,8 +18,10 @@ struct sctda_ctx {
     size_t slot_bytes[SCTDA_NUM_SLOTS];
     int64_t launches;
     int timing;                          // sctda_set_kernel_timing
-    int timed;                           // events recorded at least once
-    cudaEvent_t ev0, ev1;
+    int timed;                           // number of (begin, end) event pairs recorded by the last call
+    cudaEvent_t tev[2 * 16];             // up to 16 launches of the dominant kernel per call
+    cudaStream_t aux_stream;             // second stream for the patch pipeline (cluster.cu)
+    cudaEvent_t pipe_ev[4];
 };
 
 // Workspace slots (one live use per call; calls on one context are serialised by contract).
@@ -34,6 +36,8 @@ enum {
     WS_CLUSTER2 = 7,
     WS_CLUSTER3 = 8,
     WS_NODES = 9,
+    WS_CLUSTER4 = 10,   // second Gram buffer of the patch pipeline
+    WS_CLUSTER5 = 11,   // second batch-metadata buffer
 };
 
 static inline int sctda_fail(sctda_ctx* ctx, int code, const char* fmt, const char* a = "", long long b = 0) {
@@ -91,5 +95,6 @@ static inline void* sctda_ws(sctda_ctx* ctx, int slot, size_t bytes) {
 static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // Brackets the dominant kernel of a call with events when timing is on (see sctda_set_kernel_timing).
-#define SCTDA_TIME_BEGIN(ctx, st) do { if ((ctx)->timing) cudaEventRecord((ctx)->ev0, st); } while (0)
-#define SCTDA_TIME_END(ctx, st) do { if ((ctx)->timing) { cudaEventRecord((ctx)->ev1, st); (ctx)->timed = 1; } } while (0)
+#define SCTDA_TIME_RESET(ctx) do { if ((ctx)->timing) (ctx)->timed = 0; } while (0)
+#define SCTDA_TIME_BEGIN(ctx, st) do { if ((ctx)->timing && (ctx)->timed < 16) cudaEventRecord((ctx)->tev[2 * (ctx)->timed], st); } while (0)
+#define SCTDA_TIME_END(ctx, st) do { if ((ctx)->timing && (ctx)->timed < 16) { cudaEventRecord((ctx)->tev[2 * (ctx)->timed + 1], st); (ctx)->timed++; } } while (0)

@@ -505,6 +505,7 @@ extern "C" int32_t sctda_conn_perm_test(sctda_ctx* ctx, const sctda_graph* gr, i
                                         int64_t perm_gene_stride, const double* d_observed, double tie_rel,
                                         int32_t* d_exceed, int32_t* d_ties, double* d_scores, void* stream) {
     if (!ctx) return SCTDA_ERR_INVALID;
+    SCTDA_TIME_RESET(ctx);
     int rc = check_graph(ctx, gr);
     if (rc) return rc;
     if (G < 0 || n < 0 || (G > 0 && !d_Y) || ldy < gr->Ncells)

@@ -38,8 +38,11 @@ extern "C" int32_t sctda_ctx_destroy(sctda_ctx* ctx) {
     cudaDeviceSynchronize();
     for (int i = 0; i < SCTDA_NUM_SLOTS; ++i)
         if (ctx->slot_ptr[i]) cudaFree(ctx->slot_ptr[i]);
-    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
-    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    for (int i = 0; i < 32; ++i)
+        if (ctx->tev[i]) cudaEventDestroy(ctx->tev[i]);
+    for (int i = 0; i < 4; ++i)
+        if (ctx->pipe_ev[i]) cudaEventDestroy(ctx->pipe_ev[i]);
+    if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
     free(ctx);
     return SCTDA_OK;
 }
@@ -57,10 +60,9 @@ extern "C" int64_t sctda_launch_count(const sctda_ctx* ctx) { return ctx ? ctx->
 
 extern "C" int32_t sctda_set_kernel_timing(sctda_ctx* ctx, int32_t enabled) {
     if (!ctx) return SCTDA_ERR_INVALID;
-    if (enabled && !ctx->ev0) {
+    if (enabled && !ctx->tev[0]) {
         SCTDA_CUDA(ctx, cudaSetDevice(ctx->device));
-        SCTDA_CUDA(ctx, cudaEventCreate(&ctx->ev0));
-        SCTDA_CUDA(ctx, cudaEventCreate(&ctx->ev1));
+        for (int i = 0; i < 32; ++i) SCTDA_CUDA(ctx, cudaEventCreate(&ctx->tev[i]));
     }
     ctx->timing = enabled ? 1 : 0;
     return SCTDA_OK;
@@ -69,7 +71,13 @@ extern "C" int32_t sctda_set_kernel_timing(sctda_ctx* ctx, int32_t enabled) {
 extern "C" int32_t sctda_last_kernel_ms(sctda_ctx* ctx, float* out_ms) {
     if (!ctx || !out_ms) return SCTDA_ERR_INVALID;
     if (!ctx->timed) return sctda_fail(ctx, SCTDA_ERR_INVALID, "no timed kernel yet (sctda_set_kernel_timing)%s");
-    SCTDA_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
-    SCTDA_CUDA(ctx, cudaEventElapsedTime(out_ms, ctx->ev0, ctx->ev1));
+    float total = 0.f;
+    for (int i = 0; i < ctx->timed; ++i) {
+        float ms = 0.f;
+        SCTDA_CUDA(ctx, cudaEventSynchronize(ctx->tev[2 * i + 1]));
+        SCTDA_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->tev[2 * i], ctx->tev[2 * i + 1]));
+        total += ms;
+    }
+    *out_ms = total;
     return SCTDA_OK;
 }

@@ -59,7 +59,8 @@ struct GemmArgs {
     // single problem (nprob == 0) or batched patches
     GemmProblem single;
     int nprob;
-    const int32_t* bin_off;      // [nprob+1] member offsets
+    const int32_t* prob_bin;     // [nprob] patch index of problem p
+    const int32_t* bin_off;      // member offsets of all patches
     const int32_t* members;      // [Mtot]
     const int64_t* tile_prefix;  // [nprob+1] number of upper-triangular 128x128 tiles before problem p
     const int64_t* gram_off;     // [nprob+1] element offset of problem p's m x m output
@@ -177,14 +178,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(GemmArgs a) {
             int mid = (lo + hi) >> 1;
             if (a.tile_prefix[mid] <= t) lo = mid; else hi = mid;
         }
-        const int m = a.bin_off[lo + 1] - a.bin_off[lo];
+        const int bin = a.prob_bin[lo];
+        const int m = a.bin_off[bin + 1] - a.bin_off[bin];
         const int tn = (m + BN - 1) / BN;
         int64_t lt = t - a.tile_prefix[lo];                  // index into the upper triangle of tiles, row-major
         int ti = 0;
         while (lt >= tn - ti) { lt -= tn - ti; ++ti; }
         const int tj = ti + (int)lt;
         GemmProblem pr;
-        pr.rows_a = pr.rows_b = a.members + a.bin_off[lo];
+        pr.rows_a = pr.rows_b = a.members + a.bin_off[bin];
         pr.row0_a = pr.row0_b = 0;
         pr.na = pr.nb = m;
         pr.out = a.gram + a.gram_off[lo];
@@ -254,12 +256,12 @@ int launch_gemm(sctda_ctx* ctx, const GemmArgs& a, int64_t tiles_hint, cudaStrea
 
 // Batched patch Gram matrices for the clustering stage (cluster.cu).
 int sctda_internal_gram_bins(sctda_ctx* ctx, int G, const double* d_Xn, int64_t ldxn, int nbins,
-                             const int32_t* d_bin_off, const int32_t* d_members, const int64_t* d_tile_prefix,
-                             const int64_t* d_gram_off, double* d_gram, cudaStream_t st) {
+                             const int32_t* d_prob_bin, const int32_t* d_bin_off, const int32_t* d_members,
+                             const int64_t* d_tile_prefix, const int64_t* d_gram_off, double* d_gram, cudaStream_t st) {
     GemmArgs a;
     memset(&a, 0, sizeof(a));
     a.X = d_Xn; a.ldx = ldxn; a.G = G; a.epilogue = EPI_GRAM;
-    a.nprob = nbins; a.bin_off = d_bin_off; a.members = d_members;
+    a.nprob = nbins; a.prob_bin = d_prob_bin; a.bin_off = d_bin_off; a.members = d_members;
     a.tile_prefix = d_tile_prefix; a.gram_off = d_gram_off; a.gram = d_gram;
     return launch_gemm(ctx, a, 0, st);
 }
@@ -281,6 +283,7 @@ extern "C" int32_t sctda_gram_gather_f64(sctda_ctx* ctx, int32_t G, const double
                                          const int32_t* d_rows_a, int32_t nb, const int32_t* d_rows_b, double* d_out,
                                          int64_t ldo, void* stream) {
     if (!ctx) return SCTDA_ERR_INVALID;
+    SCTDA_TIME_RESET(ctx);
     if (G < 1 || na < 0 || nb < 0 || !d_Xn || !d_out || ldxn < G || ldo < nb)
         return sctda_fail(ctx, SCTDA_ERR_INVALID, "gram_gather: bad arguments%s");
     if ((ldxn & 1) || ((uintptr_t)d_Xn & 15))
@@ -299,6 +302,7 @@ extern "C" int32_t sctda_pairdist_rows_f64(sctda_ctx* ctx, int32_t N, int32_t G,
                                            const double* d_sq, int32_t r0, int32_t r1, int32_t metric, double* d_D,
                                            int64_t ldd, void* stream) {
     if (!ctx) return SCTDA_ERR_INVALID;
+    SCTDA_TIME_RESET(ctx);
     if (N < 1 || G < 1 || !d_Xn || !d_D || r0 < 0 || r1 < r0 || r1 > N || ldxn < G || ldd < N ||
         (metric != 0 && metric != 1) || (metric == 0 && !d_sq))
         return sctda_fail(ctx, SCTDA_ERR_INVALID, "pairdist_rows: bad arguments%s");

@@ -195,7 +195,7 @@ def cluster_sub_csr(ctx, Xn, sub_off, sub_members, max_K=5):
     return labels[:m].cpu().numpy(), K[:nb].cpu().numpy()
 
 
-def build_graph_distributed(ctx, Xd, lens, resolution, gain, equalize=True, max_K=5, metric='euclidean'):
+def build_graph_distributed(ctx, Xd, lens, resolution, gain, equalize=True, max_K=5, metric='euclidean', profile=None):
     """The graph build with the per-patch clustering sharded over the ranks of the default
     process group: X and the lens are replicated, patches are dealt by
     descending m^2, labels are exchanged by one all_gather, cover / nodes / nerve are replicated.
@@ -209,6 +209,9 @@ def build_graph_distributed(ctx, Xd, lens, resolution, gain, equalize=True, max_
     lens_d = torch.as_tensor(lens_h, dtype=torch.float64).to(dev).contiguous()
     b = [torch.from_numpy(numpy.ascontiguousarray(x)).to(dev) for x in cover_bounds(lens_h, r, gain, equalize)]
     st = _stream(dev)
+    if profile is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(torch.cuda.current_stream(dev))
     Xn, _ = row_normalize(ctx, Xd, metric)
     res = MapperDeviceResult()
     res.r = r
@@ -225,6 +228,11 @@ def build_graph_distributed(ctx, Xd, lens, resolution, gain, equalize=True, max_
     res.bin_K = torch.as_tensor(bin_K).to(dev)
     res.bin_db = None
     _finish_nodes_and_nerve(ctx, res, N, mtot)
+    if profile is not None:
+        e1.record(torch.cuda.current_stream(dev))
+        torch.cuda.current_stream(dev).synchronize()
+        profile.update({'total_ms': e0.elapsed_time(e1), 'Mtot': mtot, 'V': res.V, 'E': res.E,
+                        'gemm_ms': ctx.last_kernel_ms() if ctx.timing_enabled else None})
     return res
 
 

@@ -202,3 +202,36 @@ def test_properties_at_scale():
     assert set(map(tuple, edges.tolist())) == brute
     # nodes of one patch never connect
     assert (node_bin[edges[:, 0]] != node_bin[edges[:, 1]]).all()
+
+
+def test_patches_above_the_shared_memory_caps():
+    """One patch above the shared-memory caps of the MST / level-label kernels (10,239 cells) in
+    the same batch as small patches: the global-memory fallbacks give the oracle's labels."""
+    from oracle import mapper_oracle as mo
+    ctx = _gpu()
+    n, g, big = 12000, 24, 10800
+    X, _ = _data(n, g, seed=31)
+    rng = numpy.random.RandomState(2)
+    lens = numpy.empty((n, 2))
+    lens[:big] = 0.4 * rng.rand(big, 2)
+    lens[big:] = 0.6 + 0.4 * rng.rand(n - big, 2)
+    lens[big:big + 300, 1] = 0.3 * rng.rand(300)
+    res = _device_result(ctx, X, lens, 2, 0.1, equalize=False)
+    bin_off = res.bin_off.cpu().numpy()
+    members = res.members.cpu().numpy()
+    labels = res.labels.cpu().numpy()
+    bin_K = res.bin_K.cpu().numpy()
+    bin_db = res.bin_db.cpu().numpy()
+    bins, _ = mo.cover(lens, 2, 0.1, False)
+    sizes = [len(b) for b in bins]
+    assert max(sizes) > 10239 and 1 < sorted(sizes)[-2] < 7000
+    Xn, _ = mo.row_normalize(X, 'euclidean')
+    for b, cells in enumerate(bins):
+        assert list(members[bin_off[b]:bin_off[b + 1]]) == list(cells)
+        if len(cells) == 0:
+            assert bin_K[b] == 0
+            continue
+        lab, K, scores = mo.cluster_bin(mo.gram(Xn, cells, cells), max_K=5)
+        assert bin_K[b] == K
+        assert (labels[bin_off[b]:bin_off[b + 1]] == lab).all()
+        assert (_bits(bin_db[b, :len(scores)]) == _bits(numpy.array(scores))).all()
