@@ -278,6 +278,19 @@ def run_mapper(a, ctx, dev, steps, warmup, rank=0, world=1):
                                           'about half of `flops`, which is SURVEY.md 8d\'s algorithmic 2*G*sum m_b^2 '
                                           'without symmetry credit, so frac can exceed 1',
                         'peak_source': 'torch.matmul float64 6144^3 (cuBLAS DGEMM) probe in this run'}}
+    # end to end through the reference-facing call: host table and host lens in, networkx graph,
+    # node lists and patches out (H2D of the table, D2H of the CSR / edges, graph object built on the host)
+    if world == 1:
+        Xh = X.cpu().numpy()
+        lens_h = lens.cpu().numpy()
+        mapper.mapper_graph(Xh[:2000], lens_h[:2000], r, gain, metric=metric, verbose=False)       # warm-up
+        t0 = time.perf_counter()
+        Gx, clusters, _ = mapper.mapper_graph(Xh, lens_h, r, gain, metric=metric, verbose=False)
+        dt = time.perf_counter() - t0
+        out['e2e'] = {'value': N / dt, 'unit': 'cells/s', 'ms': 1e3 * dt, 'h2d_bytes': int(Xh.nbytes + lens_h.nbytes),
+                      'd2h_bytes': int(4 * (2 * prof['Mtot'] + 2 * prof['E'] + prof['V'] + r * r + 2)),
+                      'api': 'sctda_b200.mapper.mapper_graph(host table, host lens) -> (networkx.Graph, all_clusters, patches)'}
+        assert Gx.number_of_nodes() == prof['V'] and Gx.number_of_edges() == prof['E']
     del X
     torch.cuda.empty_cache()
     return out
@@ -403,9 +416,17 @@ def run_own(a):
     if os.path.exists(tpath):
         with open(tpath) as f:
             traffic = json.load(f).get('conn_perm_kernel_bytes_per_launch')
+    # on-chip view: with the permutation block shared, every gene*perm gathers 8*Mtot bytes of table
+    # rows from L2 plus the float32 node values of the sparse product (model, matches ncu's
+    # l1tex__m_xbar2l1tex_read_bytes to a few per cent); ceiling = measured L2 -> SM read bandwidth
+    l2_bytes_per_unit = 8.0 * dg.Mtot + 4.0 * dg.V + 4.0 * (dg.nnz + dg.V) + 4.0 * dg.Mtot / 32.0
+    l2_peak = ctx.probe_l2_read_gbs()
+    l2_ach = l2_bytes_per_unit * G * a.perms / (k_ms * 1e-3) / 1e9
     roof = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
             'traffic': traffic, 'kernel': 'conn_perm_kernel', 'kernel_ms': k_ms, 'peak_source': peak_src,
             'algorithmic_bytes_per_unit': bytes_per_unit,
+            'onchip': {'bound': 'l2', 'achieved': l2_ach, 'peak': l2_peak, 'unit': 'GB/s', 'frac': l2_ach / l2_peak,
+                       'bytes_per_unit': l2_bytes_per_unit, 'peak_source': 'sctda_probe_l2_read_gbs in this run'},
             'note': 'permutation block shared by all genes: index traffic is amortised over the gene shard, '
                     'the binding resource is the L2->SM gather of 8*Mtot bytes per gene*perm (DESIGN.md)'}
 

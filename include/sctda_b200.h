@@ -68,6 +68,12 @@ int64_t sctda_launch_count(const sctda_ctx* ctx);
 int32_t sctda_set_kernel_timing(sctda_ctx* ctx, int32_t enabled);
 int32_t sctda_last_kernel_ms(sctda_ctx* ctx, float* out_ms);
 
+/* Yard-stick for bench.py: measured L2 -> SM read bandwidth (GB/s) of this GPU, all SMs streaming a
+ * 32 MB L2-resident buffer with 16-byte loads.  The permutation kernel's gathers are served
+ * from L2, so this is the on-chip ceiling its achieved gather rate is reported against.
+ * Synchronises the host. */
+int32_t sctda_probe_l2_read_gbs(sctda_ctx* ctx, double* out_gbs);
+
 /* ---- hot path (b): connectivity permutation test ------------------------------------------- */
 
 /*
@@ -200,6 +206,8 @@ int32_t sctda_cover_fill(sctda_ctx* ctx, int32_t N, int32_t r, const int32_t* d_
 /* Per-patch clustering (mapper_graph stage 2): single linkage (MST) on squared Euclidean
  * distances between the rows of Xn, K in 2..K_max chosen by the Davies-Bouldin index
  * (stat 0 = 'db'), K_max = 2 if m <= 5 else min(m/2, max_K); a one-cell patch is one node.
+ * stat 1 = 'histgap': the classic Mapper cut instead — tree edge lengths in 10 equal bins, every
+ * edge above the first empty bin is removed (any number of clusters; d_bin_db stays NaN).
  * d_labels [total] cluster of each membership (numbered by smallest member), d_bin_K [nbins],
  * d_bin_db [nbins, 8] the index of K = 2, 3, ... (NaN where not evaluated; may be NULL).
  * Synchronises the host once (patch sizes: batching of the Gram tiles to the free memory,
@@ -222,6 +230,20 @@ int32_t sctda_nodes_fill(sctda_ctx* ctx, int32_t nbins, const int32_t* d_bin_off
 int32_t sctda_nerve_count(sctda_ctx* ctx, int32_t N, int32_t V, const int32_t* d_node_off,
                           const int32_t* d_node_members, int64_t Mtot, int64_t* d_edge_count, void* stream);
 int32_t sctda_nerve_fill(sctda_ctx* ctx, int32_t V, int32_t* d_edges, void* stream);
+
+/* ---- RootedGraph root finding (first "next" row) ------------------------------- */
+/*
+ * RootedGraph.get_dendrite (ref:1463-1479) for all V source nodes at once: hop distances from
+ * every node (BFS over the FULL symmetric adjacency CSR d_adj_off / d_adj_idx, both directions
+ * stored), nodes at the maximal distance dropped, score = -spearman(x, distance) with average
+ * ranks for ties (scipy.stats.spearmanr).  x is given through its sorted order, computed once by
+ * the caller: d_xorder [V] nodes by ascending x, d_gstart / d_gend [V] the tie group
+ * [gstart, gend) of each sorted position.  d_score [V] (NaN where undefined), d_dist [V, V]
+ * int32 hop distances (-1: unreachable) or NULL.  V <= 17,000.
+ */
+int32_t sctda_root_scores(sctda_ctx* ctx, int32_t V, const int32_t* d_adj_off, const int32_t* d_adj_idx,
+                          const int32_t* d_xorder, const int32_t* d_gstart, const int32_t* d_gend,
+                          double* d_score, int32_t* d_dist, void* stream);
 
 /*
  * Diagnostic: the permutation kernel divides with a reciprocal and one fused correction step

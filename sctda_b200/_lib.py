@@ -54,7 +54,9 @@ SIGNATURES = {
     'sctda_nodes_fill': (c_i32, [c_ptr, c_i32, c_ptr, c_ptr, c_ptr, c_ptr, c_i32, c_ptr, c_ptr, c_ptr, c_ptr]),
     'sctda_nerve_count': (c_i32, [c_ptr, c_i32, c_i32, c_ptr, c_ptr, c_i64, c_ptr, c_ptr]),
     'sctda_nerve_fill': (c_i32, [c_ptr, c_i32, c_ptr, c_ptr]),
+    'sctda_root_scores': (c_i32, [c_ptr, c_i32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     'sctda_selftest_div': (c_i32, [c_ptr, c_i64, ctypes.POINTER(c_i64)]),
+    'sctda_probe_l2_read_gbs': (c_i32, [c_ptr, ctypes.POINTER(c_f64)]),
     'sctda_node_stats': (c_i32, [c_ptr, ctypes.POINTER(Graph), c_i32, c_ptr, c_i64, c_i32, c_ptr,
                                  c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     'sctda_conn_perm_test': (c_i32, [c_ptr, ctypes.POINTER(Graph), c_i32, c_ptr, c_i64, c_i32,
@@ -117,6 +119,11 @@ class Context(object):
         ms = ctypes.c_float()
         self.check(self.lib.sctda_last_kernel_ms(self.handle, ctypes.byref(ms)))
         return float(ms.value)
+
+    def probe_l2_read_gbs(self):
+        v = c_f64()
+        self.check(self.lib.sctda_probe_l2_read_gbs(self.handle, ctypes.byref(v)))
+        return float(v.value)
 
     def workspace_bytes(self):
         return int(self.lib.sctda_workspace_bytes(self.handle))

@@ -119,6 +119,7 @@ __global__ void __launch_bounds__(256) cover_scan_kernel(const unsigned long lon
 // ---------------------------------------------------------------------------------------------
 struct ClusterArgs {
     int nbins, max_K;
+    int stat;                 // 0: Davies-Bouldin selection over 2..K_max, 1: first-empty-histogram-bin cut
     const int32_t* bin_off;
     const int32_t* prob_bin;  // [nprob] patch index of problem p of the current batch (largest first)
     int prob0;                // first problem served by this launch
@@ -327,6 +328,65 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(ClusterArgs a) {
     const int32_t* par = a.mst_parent + off;
     const int32_t* seq = a.mst_seq + off;
     int8_t* lev = m > a.lev_cap ? a.lev_g + (size_t)off * (kMaxK - 1) : (int8_t*)s_dyn;
+    if (a.stat == 1) {
+        // Histogram-gap cut (the rule BASELINE.json's north_star names; oracle cluster_bin(stat='histgap')):
+        // edge lengths h = sqrt(d2) of the m-1 tree edges, 10 equal bins between min and max, every edge
+        // in a bin above the first empty one is removed; no empty bin (or hi == lo) -> one cluster.
+        constexpr int NB = 10;
+        __shared__ int s_cnt[NB];
+        __shared__ double s_lo, s_hi;
+        if (tid < NB) s_cnt[tid] = 0;
+        double lo = INFINITY, hi = -INFINITY;
+        for (int q = tid; q < m; q += kSelThreads)
+            if (ord[q] >= 0) { const double h = sqrt(w[q]); lo = fmin(lo, h); hi = fmax(hi, h); }
+#pragma unroll
+        for (int o2 = 16; o2 > 0; o2 >>= 1) {
+            lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o2));
+            hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o2));
+        }
+        if (lane == 0) { s_rk[warp] = lo; s_cc[warp / kMaxK][warp % kMaxK] = hi; }
+        __syncthreads();
+        if (tid == 0) {
+            for (int x = 1; x < kSelThreads / 32; ++x) { lo = fmin(lo, s_rk[x]); hi = fmax(hi, s_cc[x / kMaxK][x % kMaxK]); }
+            s_lo = lo; s_hi = hi;
+        }
+        __syncthreads();
+        lo = s_lo; hi = s_hi;
+        const bool flat = !(hi > lo);
+        const double width = __ddiv_rn(__dsub_rn(hi, lo), (double)NB);
+        if (!flat)
+            for (int q = tid; q < m; q += kSelThreads)
+                if (ord[q] >= 0) atomicAdd(&s_cnt[min((int)__ddiv_rn(__dsub_rn(sqrt(w[q]), lo), width), NB - 1)], 1);
+        __syncthreads();
+        if (tid == 0) {
+            int empty = -1;
+            if (!flat)
+                for (int i = 0; i < NB && empty < 0; ++i)
+                    if (s_cnt[i] == 0) empty = i;
+            int32_t* comp = a.labels + off;
+            int32_t* scratch = (int32_t*)(a.TK + (int64_t)off * kMaxK);      // cmin [m], owner [m], rank [m]
+            int32_t* cmin = scratch, *owner = scratch + m, *rank = scratch + 2 * (int64_t)m;
+            int ncomp = 1;
+            comp[0] = 0; cmin[0] = 0;
+            for (int t = 1; t < m; ++t) {
+                const int v = seq[t];
+                bool cut = false;
+                if (empty >= 0) cut = min((int)__ddiv_rn(__dsub_rn(sqrt(w[v]), lo), width), NB - 1) > empty;
+                int c;
+                if (cut) { c = ncomp; cmin[ncomp++] = v; }
+                else { c = comp[par[v]]; if (v < cmin[c]) cmin[c] = v; }
+                comp[v] = c;
+            }
+            for (int v = 0; v < m; ++v) owner[v] = -1;
+            for (int c = 0; c < ncomp; ++c) owner[cmin[c]] = c;
+            int next = 0;
+            for (int v = 0; v < m; ++v)
+                if (owner[v] >= 0) rank[owner[v]] = next++;                      // clusters numbered by smallest member
+            for (int v = 0; v < m; ++v) comp[v] = rank[comp[v]];
+            a.bin_K[b] = ncomp;
+        }
+        return;
+    }
     // (c) the nlev heaviest tree edges: (weight desc, insertion order desc)
     for (int h = 0; h < nlev; ++h) {
         double bk = -1.0;
@@ -662,7 +722,8 @@ extern "C" int32_t sctda_bin_cluster(sctda_ctx* ctx, int32_t G, const double* d_
     if (G < 1 || nbins < 0 || !d_Xn || ldxn < G || !d_bin_off || !d_members || !d_labels || !d_bin_K)
         return sctda_fail(ctx, SCTDA_ERR_INVALID, "bin_cluster: bad arguments%s");
     if (max_K < 2 || max_K > kMaxK) return sctda_fail(ctx, SCTDA_ERR_UNSUPPORTED, "bin_cluster: max_K must be in 2..8%s");
-    if (stat != 0) return sctda_fail(ctx, SCTDA_ERR_UNSUPPORTED, "bin_cluster: only statistics='db' (0) is served%s");
+    if (stat != 0 && stat != 1)
+        return sctda_fail(ctx, SCTDA_ERR_UNSUPPORTED, "bin_cluster: statistics must be 0 ('db') or 1 ('histgap')%s");
     if ((ldxn & 1) || ((uintptr_t)d_Xn & 15))
         return sctda_fail(ctx, SCTDA_ERR_UNSUPPORTED, "bin_cluster: rows must be 16-byte aligned (even ldxn)%s");
     if (nbins == 0) return SCTDA_OK;
@@ -701,7 +762,7 @@ extern "C" int32_t sctda_bin_cluster(sctda_ctx* ctx, int32_t G, const double* d_
     unsigned char* aux = (unsigned char*)sctda_ws(ctx, WS_CLUSTER3, aux_bytes);
     if (!aux) return SCTDA_ERR_NOMEM;
     ClusterArgs a;
-    a.nbins = nbins; a.max_K = max_K; a.bin_off = d_bin_off;
+    a.nbins = nbins; a.max_K = max_K; a.stat = stat; a.bin_off = d_bin_off;
     a.T = (double*)aux;
     a.TK = a.T + M * kMaxK;
     a.mst_w = a.TK + M * kMaxK;

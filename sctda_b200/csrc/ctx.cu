@@ -81,3 +81,51 @@ extern "C" int32_t sctda_last_kernel_ms(sctda_ctx* ctx, float* out_ms) {
     *out_ms = total;
     return SCTDA_OK;
 }
+
+// ---- yard-stick: L2 -> SM read bandwidth --------------------------------------------------------
+// Every CTA streams the same L2-resident buffer with 16-byte loads (no reuse in L1: ld.global.cg).
+__global__ void __launch_bounds__(1024) l2_probe_kernel(const uint4* __restrict__ buf, size_t n16, int iters,
+                                                        unsigned* __restrict__ sink) {
+    unsigned acc = 0;
+    for (int it = 0; it < iters; ++it) {
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x * 4) {
+            uint4 v0 = __ldcg(buf + i);
+            size_t i1 = i + (size_t)gridDim.x * blockDim.x, i2 = i1 + (size_t)gridDim.x * blockDim.x,
+                   i3 = i2 + (size_t)gridDim.x * blockDim.x;
+            uint4 v1 = i1 < n16 ? __ldcg(buf + i1) : make_uint4(0, 0, 0, 0);
+            uint4 v2 = i2 < n16 ? __ldcg(buf + i2) : make_uint4(0, 0, 0, 0);
+            uint4 v3 = i3 < n16 ? __ldcg(buf + i3) : make_uint4(0, 0, 0, 0);
+            acc ^= v0.x ^ v1.y ^ v2.z ^ v3.w;
+        }
+    }
+    if (acc == 0x12345678u) *sink = acc;
+}
+
+extern "C" int32_t sctda_probe_l2_read_gbs(sctda_ctx* ctx, double* out_gbs) {
+    if (!ctx || !out_gbs) return SCTDA_ERR_INVALID;
+    SCTDA_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t bytes = (size_t)32 << 20;                       // resident in the 126 MB L2
+    unsigned char* buf = (unsigned char*)sctda_ws(ctx, WS_MISC, bytes + 64);
+    if (!buf) return SCTDA_ERR_NOMEM;
+    SCTDA_CUDA(ctx, cudaMemset(buf, 1, bytes + 64));
+    cudaEvent_t e0, e1;
+    SCTDA_CUDA(ctx, cudaEventCreate(&e0));
+    SCTDA_CUDA(ctx, cudaEventCreate(&e1));
+    const int iters = 40;
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {
+        SCTDA_CUDA(ctx, cudaEventRecord(e0));
+        l2_probe_kernel<<<ctx->sm_count * 2, 1024>>>((const uint4*)buf, bytes / 16, iters, (unsigned*)(buf + bytes));
+        SCTDA_CUDA(ctx, cudaEventRecord(e1));
+        SCTDA_CUDA(ctx, cudaEventSynchronize(e1));
+        float ms = 0.f;
+        SCTDA_CUDA(ctx, cudaEventElapsedTime(&ms, e0, e1));
+        const double gbs = (double)bytes * iters / (ms * 1e-3) / 1e9;
+        if (rep > 0 && gbs > best) best = gbs;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    SCTDA_LAUNCH_CHECK(ctx, "l2_probe_kernel");
+    *out_gbs = best;
+    return SCTDA_OK;
+}

@@ -403,9 +403,9 @@ class UnrootedGraph(object):
 
 class RootedGraph(UnrootedGraph):
     """Longitudinal data: root node, pseudo-time regression, centroid / dispersion columns
-    (ref:1449-1567, 1724-1743, 1879-1914).  Root finding (get_dendrite, ref:1463-1479) is an
-    all-pairs BFS plus one Spearman correlation per node; it is a SURVEY.md §8f "next" row
-    and runs on the host here (scipy), as does the one-off regression."""
+    (ref:1449-1567, 1724-1743, 1879-1914).  Root finding (get_dendrite, ref:1463-1479: all-pairs
+    BFS plus one Spearman correlation per node) runs on the device (rooted.cu); the one-off
+    linear regression of ref:1563-1567 is host scipy."""
 
     def __init__(self, name, table, rootlane='timepoint', shift=None, log2=True, posgl=False, csv=False,
                  groups=True, device=0):
@@ -420,27 +420,44 @@ class RootedGraph(UnrootedGraph):
         self._dist_dev = torch.from_numpy(dr.astype(numpy.float64)).to(torch.device('cuda', self.device))
         self._stats = None
 
-    def _hops(self):
-        if not hasattr(self, '_hop'):
-            self._hop = scipy.sparse.csgraph.shortest_path(self.adj_csr, method='D', unweighted=True)
-        return self._hop
+    def _root_scores(self):
+        """sctda_root_scores: (scores [V], hop distances [V, V]) for every source node."""
+        if not hasattr(self, '_rs'):
+            import ctypes
+            ctx = self._context()
+            dev = torch.device('cuda', self.device)
+            daycolor = self.get_gene(self.rootlane, ignore_log=True)[0]
+            day = numpy.array([daycolor[k] for k in self.pl])
+            x = day - day.min()                                                   # ref:1472-1475
+            order = numpy.argsort(x, kind='stable')
+            xs = x[order]
+            V = len(self.pl)
+            new_group = numpy.concatenate([[True], xs[1:] != xs[:-1]])
+            starts = numpy.nonzero(new_group)[0]
+            gid = numpy.cumsum(new_group) - 1
+            ends = numpy.concatenate([starts[1:], [V]])
+            A = scipy.sparse.csr_matrix(self.adj_csr + self.adj_csr.T)
+            A.sort_indices()
+            t = [torch.from_numpy(numpy.ascontiguousarray(a, dtype=numpy.int32)).to(dev)
+                 for a in (A.indptr, A.indices, order, starts[gid], ends[gid])]
+            score = torch.empty(V, dtype=torch.float64, device=dev)
+            dist = torch.empty((V, V), dtype=torch.int32, device=dev)
+            ctx.check(ctx.lib.sctda_root_scores(ctx.handle, V, _lib.ptr(t[0]), _lib.ptr(t[1]), _lib.ptr(t[2]), _lib.ptr(t[3]),
+                                                _lib.ptr(t[4]), _lib.ptr(score), _lib.ptr(dist),
+                                                ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+            self._rs = (score.cpu().numpy(), dist.cpu().numpy())
+        return self._rs
 
     def get_distroot(self, root):
         """ref:1454-1461: hop distance of every node of the largest component to `root`."""
-        d = self._hops()[self.pl.index(str(root))]
+        d = self._root_scores()[1][self.pl.index(str(root))]
         return {k: int(v) for k, v in zip(self.pl, d)}
 
     def get_dendrite(self):
-        """ref:1463-1479."""
-        daycolor = self.get_gene(self.rootlane, ignore_log=True)[0]
-        day = numpy.array([daycolor[k] for k in self.pl])
-        day = day - day.min()
-        H = self._hops()
-        out = {}
-        for i, k in enumerate(self.pl):
-            sel = H[i] != H[i].max()
-            out[str(k)] = -scipy.stats.spearmanr(day[sel], H[i][sel])[0] if sel.any() else float('nan')
-        return out
+        """ref:1463-1479: for every node, minus the Spearman correlation between time point and hop
+        distance over the nodes that are not at the maximal distance (all sources in one kernel)."""
+        sc = self._root_scores()[0]
+        return {str(k): float(v) for k, v in zip(self.pl, sc)}
 
     @staticmethod
     def find_root(dendritem):

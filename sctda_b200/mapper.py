@@ -22,6 +22,30 @@ def _stream(dev):
     return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
 
+_dummy = {}
+
+
+def _nonnull(t):
+    """Pointer of a device tensor; an empty tensor maps to a one-element dummy buffer."""
+    if t.numel():
+        return ctypes.c_void_p(t.data_ptr())
+    if t.device not in _dummy:
+        _dummy[t.device] = torch.zeros(16, dtype=torch.int64, device=t.device)
+    return ctypes.c_void_p(_dummy[t.device].data_ptr())
+
+
+class _Buf(object):
+    """A device array of n elements whose pointer is valid even when n == 0 (an empty torch
+    tensor reports a NULL data_ptr, which the C-ABI rejects as a missing argument)."""
+
+    def __init__(self, shape, dtype, dev):
+        n = shape[0] if isinstance(shape, tuple) else shape
+        full = (max(n, 1),) + (shape[1:] if isinstance(shape, tuple) else ())
+        self.base = torch.empty(full, dtype=dtype, device=dev)
+        self.view = self.base[:n]
+        self.ptr = ctypes.c_void_p(self.base.data_ptr())
+
+
 def _padded_device_table(X, dev):
     """float64 device copy of a cells x genes table with an even leading dimension (the
     contraction kernel stages 16-byte chunks)."""
@@ -109,8 +133,8 @@ def build_graph_device(ctx, Xd, lens, resolution, gain, equalize=True, stat='db'
     dev = Xd.device
     N, G = Xd.shape
     r = int(resolution)
-    if stat != 'db':
-        raise NotImplementedError("statistics=%r: only 'db' is served by the device path" % (stat,))
+    if stat not in ('db', 'histgap'):
+        raise NotImplementedError("statistics=%r: the device path serves 'db' and 'histgap' (the gap statistic is randomised)" % (stat,))
     if not isinstance(lens, torch.Tensor):
         lens = numpy.array(lens, dtype=numpy.float64)
     lens_d = torch.as_tensor(lens, dtype=torch.float64).to(dev).contiguous()
@@ -135,15 +159,17 @@ def build_graph_device(ctx, Xd, lens, resolution, gain, equalize=True, stat='db'
     ctx.check(ctx.lib.sctda_cover_count(ctx.handle, N, _lib.ptr(lens_d), 2, r, _lib.ptr(b[0]), _lib.ptr(b[1]),
                                         _lib.ptr(b[2]), _lib.ptr(b[3]), _lib.ptr(res.bin_off), st))
     mtot = int(res.bin_off[B].item())
-    res.members = torch.empty(max(mtot, 1), dtype=torch.int32, device=dev)[:mtot]
-    ctx.check(ctx.lib.sctda_cover_fill(ctx.handle, N, r, _lib.ptr(res.bin_off), ctypes.c_void_p(res.members.data_ptr()), st))
+    _b_members = _Buf(mtot, torch.int32, dev)
+    res.members = _b_members.view
+    ctx.check(ctx.lib.sctda_cover_fill(ctx.handle, N, r, _lib.ptr(res.bin_off), _b_members.ptr, st))
     mark('cover')
-    res.labels = torch.empty(max(mtot, 1), dtype=torch.int32, device=dev)[:mtot]
+    _b_labels = _Buf(mtot, torch.int32, dev)
+    res.labels = _b_labels.view
     res.bin_K = torch.empty(B, dtype=torch.int32, device=dev)
     res.bin_db = torch.empty((B, 8), dtype=torch.float64, device=dev)
     ctx.check(ctx.lib.sctda_bin_cluster(ctx.handle, G, _lib.ptr(Xn), int(Xn.stride(0)), B, _lib.ptr(res.bin_off),
-                                        ctypes.c_void_p(res.members.data_ptr()), int(max_K), 0,
-                                        ctypes.c_void_p(res.labels.data_ptr()), _lib.ptr(res.bin_K), _lib.ptr(res.bin_db), st))
+                                        _b_members.ptr, int(max_K), 1 if stat == 'histgap' else 0,
+                                        _b_labels.ptr, _lib.ptr(res.bin_K), _lib.ptr(res.bin_db), st))
     if profile is not None:
         profile['gemm_ms'] = ctx.last_kernel_ms() if ctx.timing_enabled else None
     mark('cluster')
@@ -152,21 +178,24 @@ def build_graph_device(ctx, Xd, lens, resolution, gain, equalize=True, stat='db'
     V = int(node_base[B].item())
     res.V = V
     res.node_off = torch.empty(V + 1, dtype=torch.int32, device=dev)
-    res.node_members = torch.empty(max(mtot, 1), dtype=torch.int32, device=dev)[:mtot]
-    res.node_bin = torch.empty(max(V, 1), dtype=torch.int32, device=dev)[:V]
-    ctx.check(ctx.lib.sctda_nodes_fill(ctx.handle, B, _lib.ptr(res.bin_off), ctypes.c_void_p(res.members.data_ptr()),
-                                       ctypes.c_void_p(res.labels.data_ptr()), _lib.ptr(node_base), V,
-                                       _lib.ptr(res.node_off), ctypes.c_void_p(res.node_members.data_ptr()),
-                                       ctypes.c_void_p(res.node_bin.data_ptr()), st))
+    _b_node_members = _Buf(mtot, torch.int32, dev)
+    res.node_members = _b_node_members.view
+    _b_node_bin = _Buf(V, torch.int32, dev)
+    res.node_bin = _b_node_bin.view
+    ctx.check(ctx.lib.sctda_nodes_fill(ctx.handle, B, _lib.ptr(res.bin_off), _b_members.ptr,
+                                       _b_labels.ptr, _lib.ptr(node_base), V,
+                                       _lib.ptr(res.node_off), _b_node_members.ptr,
+                                       _b_node_bin.ptr, st))
     mark('nodes')
     ecount = torch.zeros(1, dtype=torch.int64, device=dev)
-    ctx.check(ctx.lib.sctda_nerve_count(ctx.handle, N, V, _lib.ptr(res.node_off), ctypes.c_void_p(res.node_members.data_ptr()),
+    ctx.check(ctx.lib.sctda_nerve_count(ctx.handle, N, V, _lib.ptr(res.node_off), _b_node_members.ptr,
                                         mtot, _lib.ptr(ecount), st))
     E = int(ecount.item())
     res.E = E
-    res.edges = torch.empty((max(E, 1), 2), dtype=torch.int32, device=dev)[:E]
+    _b_edges = _Buf((E, 2), torch.int32, dev)
+    res.edges = _b_edges.view
     if E:
-        ctx.check(ctx.lib.sctda_nerve_fill(ctx.handle, V, ctypes.c_void_p(res.edges.data_ptr()), st))
+        ctx.check(ctx.lib.sctda_nerve_fill(ctx.handle, V, _b_edges.ptr, st))
     mark('nerve')
     if profile is not None:
         torch.cuda.current_stream(dev).synchronize()
@@ -220,8 +249,9 @@ def build_graph_distributed(ctx, Xd, lens, resolution, gain, equalize=True, max_
                                         _lib.ptr(b[2]), _lib.ptr(b[3]), _lib.ptr(res.bin_off), st))
     bin_off = res.bin_off.cpu().numpy()
     mtot = int(bin_off[B])
-    res.members = torch.empty(max(mtot, 1), dtype=torch.int32, device=dev)[:mtot]
-    ctx.check(ctx.lib.sctda_cover_fill(ctx.handle, N, r, _lib.ptr(res.bin_off), ctypes.c_void_p(res.members.data_ptr()), st))
+    _b_members = _Buf(mtot, torch.int32, dev)
+    res.members = _b_members.view
+    ctx.check(ctx.lib.sctda_cover_fill(ctx.handle, N, r, _lib.ptr(res.bin_off), _b_members.ptr, st))
     labels, bin_K = parallel.patch_sharded_labels(bin_off, res.members.cpu().numpy(),
                                                   lambda so, sm: cluster_sub_csr(ctx, Xn, so, sm, max_K))
     res.labels = torch.as_tensor(labels).to(dev)
@@ -245,19 +275,22 @@ def _finish_nodes_and_nerve(ctx, res, N, mtot):
     V = int(node_base[B].item())
     res.V = V
     res.node_off = torch.empty(V + 1, dtype=torch.int32, device=dev)
-    res.node_members = torch.empty(max(mtot, 1), dtype=torch.int32, device=dev)[:mtot]
-    res.node_bin = torch.empty(max(V, 1), dtype=torch.int32, device=dev)[:V]
-    ctx.check(ctx.lib.sctda_nodes_fill(ctx.handle, B, _lib.ptr(res.bin_off), ctypes.c_void_p(res.members.data_ptr()),
-                                       ctypes.c_void_p(res.labels.data_ptr()), _lib.ptr(node_base), V,
-                                       _lib.ptr(res.node_off), ctypes.c_void_p(res.node_members.data_ptr()),
-                                       ctypes.c_void_p(res.node_bin.data_ptr()), st))
+    _b_node_members = _Buf(mtot, torch.int32, dev)
+    res.node_members = _b_node_members.view
+    _b_node_bin = _Buf(V, torch.int32, dev)
+    res.node_bin = _b_node_bin.view
+    ctx.check(ctx.lib.sctda_nodes_fill(ctx.handle, B, _lib.ptr(res.bin_off), _nonnull(res.members),
+                                       _nonnull(res.labels), _lib.ptr(node_base), V,
+                                       _lib.ptr(res.node_off), _b_node_members.ptr,
+                                       _b_node_bin.ptr, st))
     ecount = torch.zeros(1, dtype=torch.int64, device=dev)
-    ctx.check(ctx.lib.sctda_nerve_count(ctx.handle, N, V, _lib.ptr(res.node_off), ctypes.c_void_p(res.node_members.data_ptr()),
+    ctx.check(ctx.lib.sctda_nerve_count(ctx.handle, N, V, _lib.ptr(res.node_off), _b_node_members.ptr,
                                         mtot, _lib.ptr(ecount), st))
     res.E = int(ecount.item())
-    res.edges = torch.empty((max(res.E, 1), 2), dtype=torch.int32, device=dev)[:res.E]
+    _b_edges = _Buf((res.E, 2), torch.int32, dev)
+    res.edges = _b_edges.view
     if res.E:
-        ctx.check(ctx.lib.sctda_nerve_fill(ctx.handle, V, ctypes.c_void_p(res.edges.data_ptr()), st))
+        ctx.check(ctx.lib.sctda_nerve_fill(ctx.handle, V, _b_edges.ptr, st))
 
 
 # ----------------------------------------------------------------------------------------------

@@ -73,23 +73,25 @@ def test_pairdist_rows(metric):
     assert (numpy.diag(D) == 0.0).all()
 
 
-def _device_result(ctx, X, lens, r, gain, equalize=True, metric='euclidean', max_K=5):
+def _device_result(ctx, X, lens, r, gain, equalize=True, metric='euclidean', max_K=5, stat='db'):
     from sctda_b200 import mapper
     Xd = mapper._padded_device_table(X, torch.device('cuda', 0))
-    return mapper.build_graph_device(ctx, Xd, lens, r, gain, equalize=equalize, max_K=max_K, metric=metric)
+    return mapper.build_graph_device(ctx, Xd, lens, r, gain, equalize=equalize, max_K=max_K, metric=metric, stat=stat)
 
 
 @pytest.mark.parametrize('case', [(400, 60, 6, 0.4, True, 'euclidean', 5), (400, 60, 5, 2.0, False, 'euclidean', 5),
                                   (900, 101, 9, 1.0, True, 'correlation', 5), (250, 40, 3, 0.3, True, 'euclidean', 8),
-                                  (120, 30, 1, 0.5, True, 'euclidean', 5)])
+                                  (120, 30, 1, 0.5, True, 'euclidean', 5), (500, 50, 4, 0.5, True, 'euclidean', 5, 'histgap'),
+                                  (700, 20, 2, 0.3, True, 'correlation', 5, 'histgap')])
 def test_graph_identical_to_oracle(case):
     from oracle import mapper_oracle as mo
     ctx = _gpu()
-    n, g, r, gain, equalize, metric, max_K = case
+    stat = case[7] if len(case) > 7 else 'db'
+    n, g, r, gain, equalize, metric, max_K = case[:7]
     X, lens = _data(n, g, seed=n + r)
     lens[5] = lens[6]                                          # duplicate lens values
     X[11] = X[10]                                              # duplicate cells (zero distances)
-    res = _device_result(ctx, X, lens, r, gain, equalize, metric, max_K)
+    res = _device_result(ctx, X, lens, r, gain, equalize, metric, max_K, stat)
     bin_off = res.bin_off.cpu().numpy()
     members = res.members.cpu().numpy()
     labels = res.labels.cpu().numpy()
@@ -103,12 +105,12 @@ def test_graph_identical_to_oracle(case):
         if len(cells) == 0:
             assert bin_K[b] == 0
             continue
-        lab, K, scores = mo.cluster_bin(mo.gram(Xn, cells, cells), max_K=max_K)
+        lab, K, scores = mo.cluster_bin(mo.gram(Xn, cells, cells), max_K=max_K, stat=stat)
         assert bin_K[b] == K, 'K of patch %d (%d cells): %r vs %r' % (b, len(cells), bin_db[b], scores)
         assert list(labels[bin_off[b]:bin_off[b + 1]]) == list(lab)
         if scores:
             assert (_bits(bin_db[b, :len(scores)]) == _bits(numpy.array(scores))).all()
-    edges, clusters, _ = mo.mapper_graph(X, lens, r, gain, equalize=equalize, max_K=max_K, metric=metric)
+    edges, clusters, _ = mo.mapper_graph(X, lens, r, gain, equalize=equalize, max_K=max_K, metric=metric, stat=stat)
     node_off = res.node_off.cpu().numpy()
     node_members = res.node_members.cpu().numpy()
     assert res.V == len(clusters)
@@ -235,3 +237,40 @@ def test_patches_above_the_shared_memory_caps():
         assert bin_K[b] == K
         assert (labels[bin_off[b]:bin_off[b + 1]] == lab).all()
         assert (_bits(bin_db[b, :len(scores)]) == _bits(numpy.array(scores))).all()
+
+
+def test_mapper_abi_errors_and_empty_inputs():
+    ctx = _gpu()
+    import ctypes
+    from sctda_b200 import _lib, mapper
+    dev = torch.device('cuda', 0)
+    X = torch.zeros((8, 6), dtype=torch.float64, device=dev)
+    lens = torch.zeros((8, 2), dtype=torch.float64, device=dev)
+    off = torch.zeros(2, dtype=torch.int32, device=dev)
+    b = torch.zeros(1, dtype=torch.float64, device=dev)
+    p = _lib.ptr
+    L = ctx.lib
+    # resolution above the served maximum
+    rc = L.sctda_cover_count(ctx.handle, 8, p(lens), 2, 129, p(b), p(b), p(b), p(b), p(off), None)
+    assert rc == -4 and b'resolution' in L.sctda_last_error(ctx.handle)
+    # NULL lens
+    assert L.sctda_cover_count(ctx.handle, 8, None, 2, 1, p(b), p(b), p(b), p(b), p(off), None) == -1
+    # max_K out of range, unsupported statistic, odd leading dimension
+    lab = torch.zeros(8, dtype=torch.int32, device=dev)
+    K = torch.zeros(1, dtype=torch.int32, device=dev)
+    mem = torch.arange(8, dtype=torch.int32, device=dev)
+    assert L.sctda_bin_cluster(ctx.handle, 6, p(X), 6, 1, p(off), p(mem), 9, 0, p(lab), p(K), None, None) == -4
+    assert L.sctda_bin_cluster(ctx.handle, 6, p(X), 6, 1, p(off), p(mem), 5, 7, p(lab), p(K), None, None) == -4
+    Xo = torch.zeros((8, 7), dtype=torch.float64, device=dev)
+    assert L.sctda_bin_cluster(ctx.handle, 7, p(Xo), 7, 1, p(off), p(mem), 5, 0, p(lab), p(K), None, None) == -4
+    # fill before count with a larger problem is refused
+    big = torch.zeros(4, dtype=torch.int32, device=dev)
+    assert L.sctda_nerve_fill(ctx.handle, 100000, p(big), None) == -1
+    # a cover in which every patch is empty (all bounds exclude the cells) and constant data
+    res = mapper.build_graph_device(ctx, X, lens.cpu().numpy(), 3, 0.5,
+                                    bounds=[numpy.full(3, 5.0), numpy.full(3, 6.0), numpy.full(3, 5.0), numpy.full(3, 6.0)])
+    assert res.V == 0 and res.E == 0 and int(res.bin_off[-1]) == 0
+    # identical cells: all distances zero, ties broken by index, every patch still splits in two
+    res = mapper.build_graph_device(ctx, X, numpy.random.RandomState(0).rand(8, 2), 1, 0.5)
+    assert res.V == 2 and res.node_members.cpu().tolist() == list(range(8))
+    assert res.node_off.cpu().tolist() == [0, 7, 8] and res.E == 0      # the oracle's tie rule: the last-inserted edge is cut
