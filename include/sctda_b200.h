@@ -231,6 +231,14 @@ int32_t sctda_nerve_count(sctda_ctx* ctx, int32_t N, int32_t V, const int32_t* d
                           const int32_t* d_node_members, int64_t Mtot, int64_t* d_edge_count, void* stream);
 int32_t sctda_nerve_fill(sctda_ctx* ctx, int32_t V, int32_t* d_edges, void* stream);
 
+/*
+ * HOST function (no GPU work): the permutation source of ref:975-976.  Fills out[rows, S] with
+ * arange(S) shuffled row after row exactly as numpy.random.shuffle does on the legacy MT19937
+ * state (key624[624], *pos as returned by numpy.random.get_state()); the state is advanced in
+ * place so that numpy.random.set_state continues the stream where the reference would be.
+ */
+int32_t sctda_mt19937_shuffle_rows(uint32_t* key624, int32_t* pos, int32_t rows, int32_t S, int32_t* out);
+
 /* ---- RootedGraph root finding (first "next" row) ------------------------------- */
 /*
  * RootedGraph.get_dendrite (ref:1463-1479) for all V source nodes at once: hop distances from

@@ -155,6 +155,62 @@ __device__ __forceinline__ double node_sum(const double* base, const int32_t* __
     return acc;
 }
 
+// ---- software-pipelined variant for the shared-permutation kernel ---------------------------
+// composite index of member m of a node ending at `end` (0 beyond the end)
+template <int KIND>
+__device__ __forceinline__ int composite_index(const int32_t* __restrict__ cols, const int32_t* perm, int m, int end) {
+    int my = 0;
+    if (m < end) {
+        my = __ldg(cols + m);
+        if (KIND == PERM_GLOBAL) my = __ldg(perm + my);
+        if (KIND == PERM_SMEM) my = perm[my];
+    }
+    return my;
+}
+
+#ifndef SCTDA_CONN_PIPELINE
+#define SCTDA_CONN_PIPELINE 0
+#endif
+#define SCTDA_LOAD8(v, my, g8)                                                  \
+    _Pragma("unroll") for (int u = 0; u < 8; ++u) {                             \
+        const int i_ = __shfl_sync(0xffffffffu, my, (g8) * 8 + u);              \
+        v[u] = __ldg(base + (size_t)(unsigned)i_ * kLanes);                     \
+    }
+#define SCTDA_ADD8(acc, v) _Pragma("unroll") for (int u = 0; u < 8; ++u) acc += v[u];
+
+// Adds the `cnt` (1..32) members whose composite indices sit in the lanes of `my`, in member
+// order, with the loads of the next group of eight issued before the adds of the current one
+// (up to 16 gathers in flight per lane).
+__device__ __forceinline__ double chunk_sum(const double* base, int my, int cnt, double acc) {
+#if SCTDA_CONN_PIPELINE
+    double va[8], vb[8];
+    if (cnt >= 8) { SCTDA_LOAD8(va, my, 0) }
+    if (cnt >= 16) { SCTDA_LOAD8(vb, my, 1) }
+    if (cnt >= 8) { SCTDA_ADD8(acc, va) }
+    if (cnt >= 24) { SCTDA_LOAD8(va, my, 2) }
+    if (cnt >= 16) { SCTDA_ADD8(acc, vb) }
+    if (cnt >= 32) { SCTDA_LOAD8(vb, my, 3) }
+    if (cnt >= 24) { SCTDA_ADD8(acc, va) }
+    if (cnt >= 32) { SCTDA_ADD8(acc, vb) }
+#else
+#pragma unroll
+    for (int g8 = 0; g8 < 4; ++g8) {
+        if (cnt >= g8 * 8 + 8) {                      // warp-uniform
+            double v[8];
+            SCTDA_LOAD8(v, my, g8)
+            SCTDA_ADD8(acc, v)
+        }
+    }
+#endif
+    if (cnt < 32 && (cnt & 7)) {
+        for (int t = cnt & ~7; t < cnt; ++t) {
+            const int i = __shfl_sync(0xffffffffu, my, t);
+            acc += __ldg(base + (size_t)(unsigned)i * kLanes);
+        }
+    }
+    return acc;
+}
+
 __device__ __forceinline__ void cp_async_4(void* smem_dst, const void* gmem_src) {
     unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gmem_src) : "memory");
@@ -267,13 +323,48 @@ __global__ void __launch_bounds__(NW * 32) conn_perm_kernel(PermArgs a) {
             }
             // ---- node values (ref:978-987) ----
             double tot_w = 0.0;
-            for (int k = w; k < a.V; k += NW) {
-                int beg = __ldg(a.node_off + k), end = __ldg(a.node_off + k + 1);
-                double acc = node_sum<KIND>(base, a.node_cols, perm_r, beg, end, lane);
-                double t1 = div_rn(acc, (double)(end - beg), __ldg(a.inv_q + k));       // ref:982/986: sum / q
-                float pmv = a.log2_mode ? pm_log2_value(t1) : (float)t1;                // ref:983/986, float32 store
-                __stcg(pm + (size_t)k * kLanes + lane, pmv);
-                tot_w += (double)pmv;                                                   // ref:984
+            if (KIND == PERM_PER_LANE) {
+                for (int k = w; k < a.V; k += NW) {
+                    int beg = __ldg(a.node_off + k), end = __ldg(a.node_off + k + 1);
+                    double acc = node_sum<KIND>(base, a.node_cols, perm_r, beg, end, lane);
+                    double t1 = div_rn(acc, (double)(end - beg), __ldg(a.inv_q + k));   // ref:982/986: sum / q
+                    float pmv = a.log2_mode ? pm_log2_value(t1) : (float)t1;            // ref:983/986, float32 store
+                    __stcg(pm + (size_t)k * kLanes + lane, pmv);
+                    tot_w += (double)pmv;                                               // ref:984
+                }
+            } else {
+                // the composite indices of the next node's first chunk are fetched while the current
+                // node is summed, the second chunk's at the start of the node
+                int k = w, beg = 0, end = 0, pref = 0;
+                if (k < a.V) {
+                    beg = __ldg(a.node_off + k);
+                    end = __ldg(a.node_off + k + 1);
+                    pref = composite_index<KIND>(a.node_cols, perm_r, beg + lane, end);
+                }
+                while (k < a.V) {
+                    const int my0 = pref;
+                    const int len = end - beg;
+                    int my1 = 0;
+                    if (len > 32) my1 = composite_index<KIND>(a.node_cols, perm_r, beg + 32 + lane, end);
+                    const int kn = k + NW;
+                    int begn = 0, endn = 0;
+                    if (kn < a.V) {
+                        begn = __ldg(a.node_off + kn);
+                        endn = __ldg(a.node_off + kn + 1);
+                        pref = composite_index<KIND>(a.node_cols, perm_r, begn + lane, endn);
+                    }
+                    double acc = chunk_sum(base, my0, min(32, len), 0.0);
+                    if (len > 32) {
+                        acc = chunk_sum(base, my1, min(32, len - 32), acc);
+                        for (int b = beg + 64; b < end; b += 32)
+                            acc = chunk_sum(base, composite_index<KIND>(a.node_cols, perm_r, b + lane, end), min(32, end - b), acc);
+                    }
+                    double t1 = div_rn(acc, (double)len, __ldg(a.inv_q + k));           // ref:982/986: sum / q
+                    float pmv = a.log2_mode ? pm_log2_value(t1) : (float)t1;            // ref:983/986, float32 store
+                    __stcg(pm + (size_t)k * kLanes + lane, pmv);
+                    tot_w += (double)pmv;                                               // ref:984
+                    k = kn; beg = begn; end = endn;
+                }
             }
             s_tot[w][lane] = tot_w;
             __syncthreads();
@@ -529,7 +620,10 @@ extern "C" int32_t sctda_conn_perm_test(sctda_ctx* ctx, const sctda_graph* gr, i
     SCTDA_CUDA(ctx, cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
     inv_size_kernel<<<(gr->V + 255) / 256, 256, 0, st>>>(gr->d_node_off, gr->V, inv_q);
     SCTDA_LAUNCH_CHECK(ctx, "inv_size_kernel");
-    constexpr int NW = 32;
+#ifndef SCTDA_CONN_WARPS
+#define SCTDA_CONN_WARPS 32
+#endif
+    constexpr int NW = SCTDA_CONN_WARPS;
     PermArgs a;
     a.V = gr->V; a.S = gr->S; a.G = G; a.n = n; a.log2_mode = log2_mode;
     a.nchunks = (n + kPermChunk - 1) / kPermChunk;

@@ -41,14 +41,22 @@ def benjamini_hochberg(pvalues):
 def reference_perm_indices(n, S, rng=None):
     """The permutation source of ref:975-976 as index arrays: row r of an n x S block is
     arange(S) shuffled by numpy.random.shuffle, rows in order, from the GLOBAL legacy
-    MT19937 stream (or `rng`).  Fisher-Yates never looks at the values, so the draws are
-    those the reference consumes and shuffled_row == row[perm[r]]."""
-    rng = numpy.random if rng is None else rng
+    MT19937 stream (or the RandomState `rng`).  Fisher-Yates never looks at the values, so the
+    draws are those the reference consumes and shuffled_row == row[perm[r]].
+    The draws are made by sctda_mt19937_shuffle_rows (the same generator and rejection rule in
+    C) on the state taken from numpy, which is then put back advanced."""
+    import ctypes
+    st = (numpy.random if rng is None else rng).get_state()
+    if st[0] != 'MT19937':
+        raise ValueError('the reference stream is the legacy MT19937 generator')
+    key = numpy.ascontiguousarray(st[1], dtype=numpy.uint32).copy()
+    pos = ctypes.c_int32(int(st[2]))
     out = numpy.empty((n, S), dtype=numpy.int32)
-    base = numpy.arange(S, dtype=numpy.int32)
-    for r in range(n):
-        out[r] = base
-        rng.shuffle(out[r])
+    lib = _lib.load()
+    rc = lib.sctda_mt19937_shuffle_rows(key.ctypes.data, ctypes.byref(pos), int(n), int(S), out.ctypes.data)
+    if rc != 0:
+        raise _lib.SctdaError(rc, 'sctda_mt19937_shuffle_rows')
+    (numpy.random if rng is None else rng).set_state((st[0], key, int(pos.value), 0, 0.0))
     return out
 
 

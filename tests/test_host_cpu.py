@@ -76,6 +76,17 @@ def test_permutation_source_is_the_reference_stream():
         numpy.random.shuffle(row)
     numpy.testing.assert_array_equal(x, (numpy.arange(37) * 1.5)[a])
     assert sorted(a[3]) == list(range(37))
+    # the C generator (sctda_mt19937_shuffle_rows) is numpy's, draw for draw, and hands the state back
+    for seed, n, S in ((1, 7, 50), (99, 33, 213), (5, 3, 1), (9, 20, 4097), (3, 2, 70000), (8, 0, 10)):
+        numpy.random.seed(seed)
+        a = graph.reference_perm_indices(n, S)
+        after_a = numpy.random.randint(0, 1 << 30, 4)
+        numpy.random.seed(seed)
+        b = co.perm_indices(n, S)
+        after_b = numpy.random.randint(0, 1 << 30, 4)
+        assert (a == b).all() and (after_a == after_b).all()
+    rs, rs2 = numpy.random.RandomState(77), numpy.random.RandomState(77)
+    assert (graph.reference_perm_indices(5, 100, rs) == co.perm_indices(5, 100, rs2)).all() and rs.rand() == rs2.rand()
 
 
 @pytest.mark.parametrize('name', ['unrooted_a', 'rooted_b'])
