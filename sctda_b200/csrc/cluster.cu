@@ -20,6 +20,9 @@
 //     with popc prefix sums into the lexicographically sorted edge list.
 #include <math.h>
 
+#include <cooperative_groups.h>
+#include <stdlib.h>
+
 #include <algorithm>
 #include <vector>
 
@@ -280,6 +283,108 @@ __global__ void __launch_bounds__(512) prim_reg_kernel(ClusterArgs a) {
             a.mst_seq[off + t + 1] = u;
         }
     }
+}
+
+// Prim for LARGE patches: one thread-block CLUSTER of 8 CTAs (4,096 threads) per patch.  Vertex q is
+// owned by cluster thread q mod 4096 (keys and parents in registers); every CTA keeps its own copy
+// of |row|^2 in shared memory.  Per step each CTA reduces its candidates, publishes (key, index) in
+// its shared memory, one cluster barrier, and every CTA reads the eight candidates through
+// distributed shared memory: the per-step latency is one row fetch of m/8 elements per CTA plus
+// one cluster barrier instead of a whole-row fetch by a single SM.
+constexpr int kClusterCtas = 8;
+
+template <int KPT>
+__global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(512) prim_cluster_kernel(ClusterArgs a) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    __shared__ double s_rk[16];
+    __shared__ int s_ri[16];
+    __shared__ double s_ck[2];                   // this CTA's candidate of step parity 0 / 1
+    __shared__ int s_ci[2];
+    const int rank = (int)cluster.block_rank();
+    const int prob = a.prob0 + blockIdx.x / kClusterCtas;
+    const int b = a.prob_bin[prob];
+    const int off = a.bin_off[b], m = a.bin_off[b + 1] - off;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int gt = rank * 512 + tid;             // cluster-wide thread index
+    constexpr int STRIDE = kClusterCtas * 512;
+    double* gpp = (double*)s_raw;
+    const double* Gm = a.gram + a.gram_off[prob];
+    for (int q = tid; q < m; q += 512) gpp[q] = Gm[(int64_t)q * m + q];
+    double key[KPT];
+    int par[KPT];
+#pragma unroll
+    for (int i = 0; i < KPT; ++i) {
+        const int q = gt + STRIDE * i;
+        key[i] = (q < m && q != 0) ? INFINITY : -1.0;
+        par[i] = -1;
+    }
+    if (gt == 0) { a.mst_parent[off] = -1; a.mst_w[off] = 0.0; a.mst_order[off] = -1; a.mst_seq[off] = 0; }
+    __syncthreads();
+    int u = 0;
+    for (int t = 0; t < m - 1; ++t) {
+        const double gu = gpp[u];
+        const double* row = Gm + (int64_t)u * m;
+        double g[KPT];
+#pragma unroll
+        for (int i = 0; i < KPT; ++i) g[i] = key[i] >= 0.0 ? row[gt + STRIDE * i] : 0.0;
+        double bk = INFINITY;
+        int bi = 0x7fffffff;
+#pragma unroll
+        for (int i = 0; i < KPT; ++i) {
+            const int q = gt + STRIDE * i;
+            double k = key[i];
+            if (k >= 0.0) {
+                const double d = dist2(gu, gpp[q], g[i]);
+                if (d < k) { k = d; key[i] = d; par[i] = u; }
+                if (k < bk || (k == bk && q < bi)) { bk = k; bi = q; }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ok = __shfl_xor_sync(0xffffffffu, bk, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ok < bk || (ok == bk && oi < bi)) { bk = ok; bi = oi; }
+        }
+        if (lane == 0) { s_rk[warp] = bk; s_ri[warp] = bi; }
+        __syncthreads();
+        const int pp = t & 1;
+        if (warp == 0) {
+            bk = lane < 16 ? s_rk[lane] : INFINITY;
+            bi = lane < 16 ? s_ri[lane] : 0x7fffffff;
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) {
+                const double ok = __shfl_xor_sync(0xffffffffu, bk, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ok < bk || (ok == bk && oi < bi)) { bk = ok; bi = oi; }
+            }
+            if (lane == 0) { s_ck[pp] = bk; s_ci[pp] = bi; }
+        }
+        cluster.sync();                           // candidates of all CTAs are published
+        bk = INFINITY;
+        bi = 0x7fffffff;
+#pragma unroll
+        for (int r = 0; r < kClusterCtas; ++r) {
+            const double ok = *cluster.map_shared_rank(&s_ck[pp], r);
+            const int oi = *cluster.map_shared_rank(&s_ci[pp], r);
+            if (ok < bk || (ok == bk && oi < bi)) { bk = ok; bi = oi; }
+        }
+        u = bi;
+        const int sel = (u % STRIDE) == gt ? (u / STRIDE) : -1;
+        int pu = -1;
+#pragma unroll
+        for (int i = 0; i < KPT; ++i) {
+            if (sel == i) { pu = par[i]; key[i] = -1.0; }
+        }
+        if (sel >= 0) {
+            a.mst_parent[off + u] = pu;
+            a.mst_w[off + u] = bk;
+            a.mst_order[off + u] = t;
+            a.mst_seq[off + t + 1] = u;
+        }
+    }
+    cluster.sync();                               // no CTA exits while its shared memory may still be read
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -779,10 +884,19 @@ extern "C" int32_t sctda_bin_cluster(sctda_ctx* ctx, int32_t G, const double* d_
     a.lev_cap = (80 * 1024 - 16) / (kMaxK - 1);
     static bool attr_set = false;
     if (!attr_set) {
-        SCTDA_CUDA(ctx, cudaFuncSetAttribute(prim_reg_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        SCTDA_CUDA(ctx, cudaFuncSetAttribute(prim_cluster_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024 - 1024));
+        SCTDA_CUDA(ctx, cudaFuncSetAttribute(prim_cluster_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 136 * 1024));
         SCTDA_CUDA(ctx, cudaFuncSetAttribute(prim_reg_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         SCTDA_CUDA(ctx, cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
         attr_set = true;
+    }
+    // size classes of the MST kernels (a test hook lowers them so that small inputs reach every kernel)
+    int thr_mid = 4096, thr_big = 16384, thr_huge = 28000;
+    if (const char* e = getenv("SCTDA_TEST_PRIM_THRESHOLDS")) {
+        int x = 0, y = 0, z = 0;
+        if (sscanf(e, "%d,%d,%d", &x, &y, &z) == 3 && 0 < x && x <= y && y <= z && x <= 4096 && y <= 16384 && z <= 28000) {
+            thr_mid = x; thr_big = y; thr_huge = z;
+        }
     }
     if (!ctx->aux_stream) {
         SCTDA_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
@@ -840,24 +954,32 @@ extern "C" int32_t sctda_bin_cluster(sctda_ctx* ctx, int32_t G, const double* d_
         if (rc) return rc;
         SCTDA_CUDA(ctx, cudaEventRecord(ctx->pipe_ev[k], st));
         SCTDA_CUDA(ctx, cudaStreamWaitEvent(aux_st, ctx->pipe_ev[k], 0));
-        // MST: patches are sorted by size; [0,n_huge) above 16,384 cells (generic kernel, state in
-        // global memory), [n_huge,n_mid) above 4,096 (32 register keys per thread), the rest 8
-        int n_huge = 0, n_mid = 0;
+        // MST: patches are sorted by size; [0,n_huge) above 28,000 cells (generic kernel, state in
+        // global memory), [n_huge,n_big) above 16,384 and [n_big,n_mid) above 4,096 (one cluster of 8
+        // CTAs per patch, 8 or 4 register keys per thread), the rest one CTA with 8 register keys
+        int n_huge = 0, n_big = 0, n_mid = 0;
         for (size_t j = bt.pos; j < bt.end; ++j) {
             const int m = h_off[order[j] + 1] - h_off[order[j]];
-            if (m > 16384) ++n_huge;
-            if (m > 4096) ++n_mid;
+            if (m > thr_huge) ++n_huge;
+            if (m > thr_big) ++n_big;
+            if (m > thr_mid) ++n_mid;
         }
         if (n_huge) {
             a.prob0 = 0;
             prim_kernel<<<n_huge, 256, 16, aux_st>>>(a);
             SCTDA_LAUNCH_CHECK(ctx, "prim_kernel");
         }
-        if (n_mid > n_huge) {
+        if (n_big > n_huge) {
             a.prob0 = n_huge;
             const int mm = h_off[order[bt.pos + n_huge] + 1] - h_off[order[bt.pos + n_huge]];
-            prim_reg_kernel<32><<<n_mid - n_huge, 512, (size_t)mm * 12 + 16, aux_st>>>(a);
-            SCTDA_LAUNCH_CHECK(ctx, "prim_reg_kernel<32>");
+            prim_cluster_kernel<8><<<(n_big - n_huge) * kClusterCtas, 512, (size_t)mm * 8 + 16, aux_st>>>(a);
+            SCTDA_LAUNCH_CHECK(ctx, "prim_cluster_kernel<8>");
+        }
+        if (n_mid > n_big) {
+            a.prob0 = n_big;
+            const int mm = h_off[order[bt.pos + n_big] + 1] - h_off[order[bt.pos + n_big]];
+            prim_cluster_kernel<4><<<(n_mid - n_big) * kClusterCtas, 512, (size_t)mm * 8 + 16, aux_st>>>(a);
+            SCTDA_LAUNCH_CHECK(ctx, "prim_cluster_kernel<4>");
         }
         if (nb > n_mid) {
             a.prob0 = n_mid;

@@ -274,3 +274,26 @@ def test_mapper_abi_errors_and_empty_inputs():
     res = mapper.build_graph_device(ctx, X, numpy.random.RandomState(0).rand(8, 2), 1, 0.5)
     assert res.V == 2 and res.node_members.cpu().tolist() == list(range(8))
     assert res.node_off.cpu().tolist() == [0, 7, 8] and res.E == 0      # the oracle's tie rule: the last-inserted edge is cut
+
+
+def test_every_mst_kernel_gives_the_same_graph(monkeypatch):
+    """The four MST kernels (one CTA with register keys, clusters of 8 CTAs with 4 / 8 keys per
+    thread, the generic global-memory kernel) are selected by patch size; the test hook lowers the
+    size classes so that one small input reaches all of them, and the graph must not change."""
+    from oracle import mapper_oracle as mo
+    ctx = _gpu()
+    X, lens = _data(900, 32, seed=77)
+    edges, clusters, _ = mo.mapper_graph(X, lens, 3, 0.8)
+    sizes = sorted(len(p) for p in mo.cover(lens, 3, 0.8)[0])
+    assert sizes[0] < 120 and sizes[-1] > 330
+    for thr in (None, '150,250,400', '100,200,300', '60,61,62'):
+        if thr is None:
+            monkeypatch.delenv('SCTDA_TEST_PRIM_THRESHOLDS', raising=False)
+        else:
+            monkeypatch.setenv('SCTDA_TEST_PRIM_THRESHOLDS', thr)
+        res = _device_result(ctx, X, lens, 3, 0.8)
+        off = res.node_off.cpu().numpy()
+        mem = res.node_members.cpu().numpy()
+        assert res.V == len(clusters)
+        assert all(list(mem[off[k]:off[k + 1]]) == list(c) for k, c in enumerate(clusters)), thr
+        assert [tuple(e) for e in res.edges.cpu().numpy().tolist()] == edges
