@@ -170,6 +170,12 @@ int32_t sctda_conn_perm_test(sctda_ctx* ctx, const sctda_graph* graph,
  * choice the call sites leave open are stated in oracle/mapper_oracle.py.
  * Variable-size outputs use a count call (sizes to the device, read by the caller) then a fill
  * call; the context keeps the intermediate state between the two.
+ *
+ * Row padding contract of every entry point that takes (G, d_Xn, ldxn): ldxn must be even.  Rows
+ * are staged in 16-byte chunks with the tail zero-filled by the library.  With the environment
+ * switch SCTDA_GEMM_TMA_BULK=1 and ldxn >= 16*ceil(G/16), rows are staged with 128-byte TMA bulk
+ * copies instead and the columns G .. 16*ceil(G/16)-1 of every row MUST BE ZERO (this is how
+ * sctda_row_normalize_f64 writes them); measured slower, kept for experiments.
  */
 
 /* Xn = X (mode 0, metric 'euclidean') or the centred, unit-norm rows of X (mode 1, 'correlation';

@@ -38,39 +38,26 @@ constexpr int kMaxK = 8;            // largest max_K served
 constexpr int kMaxRes = 128;        // largest resolution served (two 64-bit mask words per axis)
 
 // ---------------------------------------------------------------------------------------------
-// exclusive scan, one CTA: out[0] = 0, out[i+1] = out[i] + f(in[i]); optional max of in[]
+// exclusive scan, one CTA: out[0] = 0, out[i+1] = out[i] + in[i]
 // ---------------------------------------------------------------------------------------------
-enum { MAP_ID = 0, MAP_TILES = 1, MAP_SQUARE = 2 };
-
 template <typename TOut>
-__global__ void __launch_bounds__(1024) scan_kernel(const int32_t* __restrict__ in, int64_t n, int map,
-                                                    TOut* __restrict__ out, int32_t* __restrict__ out_max) {
+__global__ void __launch_bounds__(1024) scan_kernel(const int32_t* __restrict__ in, int64_t n, TOut* __restrict__ out) {
     __shared__ long long s_sum[1024];
-    __shared__ int s_max[1024];
     const int t = threadIdx.x;
     const int64_t per = (n + 1023) / 1024;
     const int64_t lo = (int64_t)t * per, hi = lo + per < n ? lo + per : n;
-    auto f = [map](int32_t v) -> long long {
-        if (map == MAP_TILES) { long long q = (v + 127) / 128; return q * (q + 1) / 2; }   // upper-triangular tiles
-        if (map == MAP_SQUARE) return (long long)v * v;
-        return v;
-    };
     long long s = 0;
-    int mx = 0;
-    for (int64_t i = lo; i < hi; ++i) { s += f(in[i]); mx = max(mx, in[i]); }
+    for (int64_t i = lo; i < hi; ++i) s += in[i];
     s_sum[t] = s;
-    s_max[t] = mx;
     __syncthreads();
     if (t == 0) {
         long long run = 0;
-        int m2 = 0;
-        for (int i = 0; i < 1024; ++i) { long long v = s_sum[i]; s_sum[i] = run; run += v; m2 = max(m2, s_max[i]); }
+        for (int i = 0; i < 1024; ++i) { long long v = s_sum[i]; s_sum[i] = run; run += v; }
         out[n] = (TOut)run;
-        if (out_max) *out_max = m2;
     }
     __syncthreads();
     long long run = s_sum[t];
-    for (int64_t i = lo; i < hi; ++i) { out[i] = (TOut)run; run += f(in[i]); }
+    for (int64_t i = lo; i < hi; ++i) { out[i] = (TOut)run; run += in[i]; }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -799,7 +786,7 @@ extern "C" int32_t sctda_cover_count(sctda_ctx* ctx, int32_t N, const double* d_
     }
     cover_scan_kernel<false><<<(unsigned)cdiv64((int64_t)B * 32, 256), 256, 0, st>>>(masks, N, r, counts, nullptr, nullptr);
     SCTDA_LAUNCH_CHECK(ctx, "cover_scan_kernel<count>");
-    scan_kernel<int32_t><<<1, 1024, 0, st>>>(counts, B, MAP_ID, d_bin_off, nullptr);
+    scan_kernel<int32_t><<<1, 1024, 0, st>>>(counts, B, d_bin_off);
     SCTDA_LAUNCH_CHECK(ctx, "scan_kernel");
     return SCTDA_OK;
 }
@@ -882,13 +869,12 @@ extern "C" int32_t sctda_bin_cluster(sctda_ctx* ctx, int32_t G, const double* d_
     a.labels = d_labels; a.bin_K = d_bin_K; a.bin_db = db;
     a.prim_cap = 0;                               // the generic kernel keeps its state in global memory
     a.lev_cap = (80 * 1024 - 16) / (kMaxK - 1);
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!(ctx->attr_done & 1u)) {
         SCTDA_CUDA(ctx, cudaFuncSetAttribute(prim_cluster_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024 - 1024));
         SCTDA_CUDA(ctx, cudaFuncSetAttribute(prim_cluster_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 136 * 1024));
         SCTDA_CUDA(ctx, cudaFuncSetAttribute(prim_reg_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         SCTDA_CUDA(ctx, cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
-        attr_set = true;
+        ctx->attr_done |= 1u;
     }
     // size classes of the MST kernels (a test hook lowers them so that small inputs reach every kernel)
     int thr_mid = 4096, thr_big = 16384, thr_huge = 28000;
@@ -1003,7 +989,7 @@ extern "C" int32_t sctda_nodes_count(sctda_ctx* ctx, int32_t nbins, const int32_
     if (!ctx) return SCTDA_ERR_INVALID;
     if (nbins < 0 || !d_bin_K || !d_node_base) return sctda_fail(ctx, SCTDA_ERR_INVALID, "nodes_count: bad arguments%s");
     SCTDA_CUDA(ctx, cudaSetDevice(ctx->device));
-    scan_kernel<int32_t><<<1, 1024, 0, (cudaStream_t)stream>>>(d_bin_K, nbins, MAP_ID, d_node_base, nullptr);
+    scan_kernel<int32_t><<<1, 1024, 0, (cudaStream_t)stream>>>(d_bin_K, nbins, d_node_base);
     SCTDA_LAUNCH_CHECK(ctx, "scan_kernel<nodes>");
     return SCTDA_OK;
 }
@@ -1028,7 +1014,7 @@ extern "C" int32_t sctda_nodes_fill(sctda_ctx* ctx, int32_t nbins, const int32_t
     node_scan_kernel<false><<<blocks, 256, 0, st>>>(V, d_node_bin, node_label, d_bin_off, d_members, d_labels, sizes,
                                                     nullptr, nullptr);
     SCTDA_LAUNCH_CHECK(ctx, "node_scan_kernel<count>");
-    scan_kernel<int32_t><<<1, 1024, 0, st>>>(sizes, V, MAP_ID, d_node_off, nullptr);
+    scan_kernel<int32_t><<<1, 1024, 0, st>>>(sizes, V, d_node_off);
     SCTDA_LAUNCH_CHECK(ctx, "scan_kernel<node sizes>");
     node_scan_kernel<true><<<blocks, 256, 0, st>>>(V, d_node_bin, node_label, d_bin_off, d_members, d_labels, nullptr,
                                                    d_node_off, d_node_members);
@@ -1063,7 +1049,7 @@ extern "C" int32_t sctda_nerve_count(sctda_ctx* ctx, int32_t N, int32_t V, const
         cell_count_kernel<<<(unsigned)cdiv64(Mtot, 256), 256, 0, st>>>(Mtot, d_node_members, cursor);
         SCTDA_LAUNCH_CHECK(ctx, "cell_count_kernel");
     }
-    scan_kernel<int32_t><<<1, 1024, 0, st>>>(cursor, N, MAP_ID, cell_off, nullptr);
+    scan_kernel<int32_t><<<1, 1024, 0, st>>>(cursor, N, cell_off);
     SCTDA_LAUNCH_CHECK(ctx, "scan_kernel<cells>");
     SCTDA_CUDA(ctx, cudaMemsetAsync(cursor, 0, (size_t)N * 4, st));
     const unsigned vblocks = (unsigned)cdiv64((int64_t)V * 32, 256);
@@ -1073,7 +1059,7 @@ extern "C" int32_t sctda_nerve_count(sctda_ctx* ctx, int32_t N, int32_t V, const
     SCTDA_LAUNCH_CHECK(ctx, "pair_kernel");
     edge_scan_kernel<false><<<vblocks, 256, 0, st>>>(V, W, bits, row_cnt, nullptr, nullptr);
     SCTDA_LAUNCH_CHECK(ctx, "edge_scan_kernel<count>");
-    scan_kernel<int64_t><<<1, 1024, 0, st>>>(row_cnt, V, MAP_ID, row_off, nullptr);
+    scan_kernel<int64_t><<<1, 1024, 0, st>>>(row_cnt, V, row_off);
     SCTDA_LAUNCH_CHECK(ctx, "scan_kernel<rows>");
     SCTDA_CUDA(ctx, cudaMemcpyAsync(d_edge_count, row_off + V, 8, cudaMemcpyDeviceToDevice, st));
     return SCTDA_OK;

@@ -20,6 +20,7 @@ struct sctda_ctx {
     int timing;                          // sctda_set_kernel_timing
     int timed;                           // number of (begin, end) event pairs recorded by the last call
     cudaEvent_t tev[2 * 16];             // up to 16 launches of the dominant kernel per call
+    unsigned attr_done;                  // per-context (= per-device) one-time kernel attribute setup, one bit per file
     cudaStream_t aux_stream;             // second stream for the patch pipeline (cluster.cu)
     cudaEvent_t pipe_ev[4];
 };
@@ -29,7 +30,6 @@ enum {
     WS_ET = 0,        // transformed, transposed expression tiles
     WS_PM = 1,        // per-CTA node value scratch
     WS_MISC = 2,
-    WS_DIST_XN = 3,   // normalised rows for the distance kernel
     WS_COVER = 4,
     WS_CLUSTER = 5,
     WS_NERVE = 6,

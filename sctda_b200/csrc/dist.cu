@@ -8,13 +8,18 @@
 //
 // Design (sm_100a).  tcgen05 has no FP64 kind, so the one dense contraction of the path runs
 // on the FP64 tensor pipe through warp-level mma.sync.m8n8k4 (DMMA): 128x128 CTA tile, 8 warps
-// of 32x64, K staged 16 columns at a time through a 3-stage cp.async ring.  Rows are GATHERED
-// (index lists), which a tiled TMA box cannot express, so the staging is 16-byte cp.async with
-// zero-fill on the K tail; shared-memory rows are padded to 20 doubles so that the 8x4 fragment
-// loads of each half warp hit 32 distinct banks.  K is walked sequentially with no split-K:
+// of 32x64, K staged 16 columns at a time through a 3-stage ring.  Rows are GATHERED (index
+// lists), which a tiled TMA box cannot express.  Two stagings exist: 16-byte cp.async with
+// zero-fill on the K tail (default), and one-dimensional TMA bulk copies (cp.async.bulk, one
+// 128-byte row segment each, SASS UBLKCP, completing on the stage's mbarrier; needs rows
+// zero-padded to a multiple of 16 columns).  The bulk path is bit-identical but measured 22 %
+// slower on these short segments and is therefore opt-in (see launch_gemm).
+// Shared-memory rows are padded to 20 doubles so that the 8x4 fragment loads of each half warp
+// hit 32 distinct banks.  K is walked sequentially with no split-K:
 // every output element is ONE chain of fused multiply-adds over k ascending, which makes the
 // result reproducible bit for bit by a scalar fma loop (oracle/mapper_oracle.c).
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -34,6 +39,32 @@ __device__ __forceinline__ void cp_async_16_zfill(void* smem_dst, const void* gm
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// ---- TMA bulk copies (cp.async.bulk, SASS UBLKCP) completing on an mbarrier -------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"((unsigned)__cvta_generic_to_shared(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+                 : "memory");
+}
 
 __device__ __forceinline__ void dmma_884(double& d0, double& d1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -67,8 +98,12 @@ struct GemmArgs {
     double* gram;
 };
 
+// BULK: every K stage is a full 16 columns (the caller guarantees zero padding up to a multiple
+// of 16) and is staged by warp 0 with one 128-byte TMA bulk copy per row, completing on the
+// stage's mbarrier; `it` counts the K stages this CTA has consumed (stage = it % 3, parity from it / 3).
+template <bool BULK>
 __device__ __forceinline__ void gemm_tile(const GemmArgs& a, const GemmProblem& pr, int ti, int tj, double* smem,
-                                          bool mirror) {
+                                          bool mirror, uint64_t* bars, unsigned& it) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp & 3, wn = warp >> 2;                 // 4 x 2 warps, warp tile 32 x 64
     const int m0 = ti * BM, n0 = tj * BN;
@@ -88,6 +123,23 @@ __device__ __forceinline__ void gemm_tile(const GemmArgs& a, const GemmProblem& 
         dst_off[i] = r * LDS + q * 2;
     }
     const int ksteps = (a.G + BK - 1) / BK;
+    // bulk path: thread t copies row (t & 127) of A (t < 128) or of B: one 128-byte TMA bulk copy per
+    // thread and stage (the copy instruction is warp-uniform in hardware, so 32 lanes are 32 issues)
+    const double* bulk_row = nullptr;
+    const int bulk_dst = ((tid >> 7) ? BM * LDS : 0) + (tid & 127) * LDS;
+    if (BULK) {
+        const int r = tid & 127;
+        if (tid < 128) {
+            const int ra = min(m0 + r, pr.na - 1);
+            bulk_row = a.X + (pr.rows_a ? (int64_t)pr.rows_a[ra] : (int64_t)(pr.row0_a + ra)) * a.ldx;
+        } else {
+            const int rb = min(n0 + r, pr.nb - 1);
+            bulk_row = a.X + (pr.rows_b ? (int64_t)pr.rows_b[rb] : (int64_t)(pr.row0_b + rb)) * a.ldx;
+        }
+    }
+    auto issue_bulk = [&](int ks, unsigned slot) {            // all threads; expect_tx was posted by thread 0
+        bulk_copy_g2s(smem + (size_t)slot * STAGE_DOUBLES + bulk_dst, bulk_row + ks * BK, BK * 8, bars + slot);
+    };
     auto issue = [&](int ks) {
         double* sA = smem + (size_t)(ks % STAGES) * STAGE_DOUBLES;
         double* sB = sA + BM * LDS;
@@ -107,19 +159,36 @@ __device__ __forceinline__ void gemm_tile(const GemmArgs& a, const GemmProblem& 
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
+    if (BULK) {
+        if (tid == 0)
+            for (int s = 0; s < STAGES - 1 && s < ksteps; ++s) mbar_expect_tx(bars + (it + s) % STAGES, (BM + BN) * BK * 8);
+        __syncthreads();
+        for (int s = 0; s < STAGES - 1 && s < ksteps; ++s) issue_bulk(s, (it + s) % STAGES);
+    } else {
 #pragma unroll
-    for (int s = 0; s < STAGES - 1; ++s) {
-        if (s < ksteps) issue(s);
-        cp_async_commit();
+        for (int s = 0; s < STAGES - 1; ++s) {
+            if (s < ksteps) issue(s);
+            cp_async_commit();
+        }
     }
     const int fr = lane >> 2, fc = lane & 3;
     for (int ks = 0; ks < ksteps; ++ks) {
-        cp_async_wait<STAGES - 2>();
-        __syncthreads();
-        if (ks + STAGES - 1 < ksteps) issue(ks + STAGES - 1);
-        cp_async_commit();
-        const double* sA = smem + (size_t)(ks % STAGES) * STAGE_DOUBLES + (wm * 32 + fr) * LDS + fc;
-        const double* sB = smem + (size_t)(ks % STAGES) * STAGE_DOUBLES + BM * LDS + (wn * 64 + fr) * LDS + fc;
+        const unsigned slot = BULK ? (it + ks) % STAGES : ks % STAGES;
+        if (BULK) {
+            const bool more = ks + STAGES - 1 < ksteps;
+            const unsigned nslot = (it + ks + STAGES - 1) % STAGES;
+            if (tid == 0 && more) mbar_expect_tx(bars + nslot, (BM + BN) * BK * 8);   // its previous phase was consumed by all
+            mbar_wait(bars + slot, ((it + ks) / STAGES) & 1);
+            __syncthreads();                                  // everybody is done with the slot refilled below
+            if (more) issue_bulk(ks + STAGES - 1, nslot);
+        } else {
+            cp_async_wait<STAGES - 2>();
+            __syncthreads();
+            if (ks + STAGES - 1 < ksteps) issue(ks + STAGES - 1);
+            cp_async_commit();
+        }
+        const double* sA = smem + (size_t)slot * STAGE_DOUBLES + (wm * 32 + fr) * LDS + fc;
+        const double* sB = smem + (size_t)slot * STAGE_DOUBLES + BM * LDS + (wn * 64 + fr) * LDS + fc;
 #pragma unroll
         for (int kk = 0; kk < BK / 4; ++kk) {
             double fa[4], fb[8];
@@ -133,7 +202,8 @@ __device__ __forceinline__ void gemm_tile(const GemmArgs& a, const GemmProblem& 
                 for (int j = 0; j < 8; ++j) dmma_884(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
         }
     }
-    cp_async_wait<0>();
+    if (!BULK) cp_async_wait<0>();
+    it += (unsigned)ksteps;
     __syncthreads();                                          // smem is reused by the next tile
     // epilogue: thread holds rows fr (+8*i), columns 2*fc, 2*fc+1 (+8*j) of its warp tile
 #pragma unroll
@@ -162,13 +232,23 @@ __device__ __forceinline__ void gemm_tile(const GemmArgs& a, const GemmProblem& 
     }
 }
 
+template <bool BULK>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(GemmArgs a) {
     extern __shared__ __align__(16) double smem[];
+    __shared__ __align__(8) uint64_t bars[STAGES];
+    unsigned it = 0;
+    if (BULK) {
+        if (threadIdx.x == 0) {
+            for (int s = 0; s < STAGES; ++s) mbar_init(bars + s, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+    }
     if (a.nprob == 0) {
         const int tn = (a.single.nb + BN - 1) / BN;
         const int64_t total = (int64_t)((a.single.na + BM - 1) / BM) * tn;
         for (int64_t t = blockIdx.x; t < total; t += gridDim.x)
-            gemm_tile(a, a.single, (int)(t / tn), (int)(t % tn), smem, false);
+            gemm_tile<BULK>(a, a.single, (int)(t / tn), (int)(t % tn), smem, false, bars, it);
         return;
     }
     const int64_t total = a.tile_prefix[a.nprob];
@@ -191,7 +271,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(GemmArgs a) {
         pr.na = pr.nb = m;
         pr.out = a.gram + a.gram_off[lo];
         pr.ldo = m;
-        gemm_tile(a, pr, ti, tj, smem, ti != tj);
+        gemm_tile<BULK>(a, pr, ti, tj, smem, ti != tj, bars, it);
     }
 }
 
@@ -236,17 +316,24 @@ __global__ void __launch_bounds__(256) row_normalize_kernel(const double* __rest
     if (lane == 0 && sq) sq[row] = s2;
 }
 
-int launch_gemm(sctda_ctx* ctx, const GemmArgs& a, int64_t tiles_hint, cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        SCTDA_CUDA(ctx, cudaFuncSetAttribute(gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
-        attr_set = true;
+// bulk: the rows are zero-padded to a multiple of 16 columns (ldx >= roundup16(G)), every K stage is full
+int launch_gemm(sctda_ctx* ctx, const GemmArgs& a, int64_t tiles_hint, cudaStream_t st, bool bulk) {
+    if (!(ctx->attr_done & 2u)) {
+        SCTDA_CUDA(ctx, cudaFuncSetAttribute(gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
+        SCTDA_CUDA(ctx, cudaFuncSetAttribute(gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
+        ctx->attr_done |= 2u;
     }
     int64_t grid = tiles_hint > 0 ? tiles_hint : ctx->sm_count;
     if (grid > ctx->sm_count) grid = ctx->sm_count;          // persistent: one CTA per SM
     if (grid < 1) grid = 1;
     SCTDA_TIME_BEGIN(ctx, st);
-    gemm_kernel<<<(unsigned)grid, GEMM_THREADS, GEMM_SMEM, st>>>(a);
+    // Measured on B200 (config 2 / config 3 patch Gram matrices): the TMA bulk-copy staging is 22 %
+    // SLOWER than 16-byte cp.async for these 128-byte gathered row segments (UBLKCP is a
+    // warp-uniform instruction: 256 serialised issues per stage against 2,048 vector LDGSTS lanes),
+    // so it is opt-in (SCTDA_GEMM_TMA_BULK=1) and cp.async stays the default.
+    static const bool want_bulk = getenv("SCTDA_GEMM_TMA_BULK") && atoi(getenv("SCTDA_GEMM_TMA_BULK")) != 0;
+    if (bulk && want_bulk) gemm_kernel<true><<<(unsigned)grid, GEMM_THREADS, GEMM_SMEM, st>>>(a);
+    else gemm_kernel<false><<<(unsigned)grid, GEMM_THREADS, GEMM_SMEM, st>>>(a);
     SCTDA_TIME_END(ctx, st);
     SCTDA_LAUNCH_CHECK(ctx, "gemm_kernel");
     return SCTDA_OK;
@@ -263,7 +350,7 @@ int sctda_internal_gram_bins(sctda_ctx* ctx, int G, const double* d_Xn, int64_t 
     a.X = d_Xn; a.ldx = ldxn; a.G = G; a.epilogue = EPI_GRAM;
     a.nprob = nbins; a.prob_bin = d_prob_bin; a.bin_off = d_bin_off; a.members = d_members;
     a.tile_prefix = d_tile_prefix; a.gram_off = d_gram_off; a.gram = d_gram;
-    return launch_gemm(ctx, a, 0, st);
+    return launch_gemm(ctx, a, 0, st, ldxn >= ((int64_t)G + 15) / 16 * 16);
 }
 
 extern "C" int32_t sctda_row_normalize_f64(sctda_ctx* ctx, int32_t N, int32_t G, const double* d_X, int64_t ldx,
@@ -295,7 +382,7 @@ extern "C" int32_t sctda_gram_gather_f64(sctda_ctx* ctx, int32_t G, const double
     a.X = d_Xn; a.ldx = ldxn; a.G = G; a.epilogue = EPI_GRAM;
     a.single.rows_a = d_rows_a; a.single.rows_b = d_rows_b; a.single.na = na; a.single.nb = nb;
     a.single.out = d_out; a.single.ldo = ldo;
-    return launch_gemm(ctx, a, cdiv64(na, BM) * cdiv64(nb, BN), (cudaStream_t)stream);
+    return launch_gemm(ctx, a, cdiv64(na, BM) * cdiv64(nb, BN), (cudaStream_t)stream, ldxn >= ((int64_t)G + 15) / 16 * 16);
 }
 
 extern "C" int32_t sctda_pairdist_rows_f64(sctda_ctx* ctx, int32_t N, int32_t G, const double* d_Xn, int64_t ldxn,
@@ -316,5 +403,5 @@ extern "C" int32_t sctda_pairdist_rows_f64(sctda_ctx* ctx, int32_t N, int32_t G,
     a.epilogue = metric == 0 ? EPI_EUCLID : EPI_CORR;
     a.single.row0_a = r0; a.single.na = r1 - r0; a.single.row0_b = 0; a.single.nb = N;
     a.single.out = d_D; a.single.ldo = ldd;
-    return launch_gemm(ctx, a, cdiv64(r1 - r0, BM) * cdiv64(N, BN), (cudaStream_t)stream);
+    return launch_gemm(ctx, a, cdiv64(r1 - r0, BM) * cdiv64(N, BN), (cudaStream_t)stream, ldxn >= ((int64_t)G + 15) / 16 * 16);
 }

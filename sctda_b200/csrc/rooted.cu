@@ -122,10 +122,9 @@ extern "C" int32_t sctda_root_scores(sctda_ctx* ctx, int32_t V, const int32_t* d
     const size_t smem = ((size_t)3 * V + 4) * sizeof(int);
     if (smem > 200 * 1024) return sctda_fail(ctx, SCTDA_ERR_UNSUPPORTED, "root_scores: more than 17,000 nodes is not served%s");
     SCTDA_CUDA(ctx, cudaSetDevice(ctx->device));
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!(ctx->attr_done & 4u)) {
         SCTDA_CUDA(ctx, cudaFuncSetAttribute(root_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
+        ctx->attr_done |= 4u;
     }
     root_score_kernel<<<V, RT, smem, (cudaStream_t)stream>>>(V, d_adj_off, d_adj_idx, d_xorder, d_gstart, d_gend, d_score, d_dist);
     SCTDA_LAUNCH_CHECK(ctx, "root_score_kernel");

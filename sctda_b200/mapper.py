@@ -65,7 +65,7 @@ def row_normalize(ctx, Xd, metric):
     """sctda_row_normalize_f64: (Xn [N, G] view of an even-ld buffer, sq [N])."""
     dev = Xd.device
     n, g = Xd.shape
-    ld = g + (g % 2)
+    ld = (g + 15) // 16 * 16          # zero-padded to a multiple of 16 columns: TMA bulk-copy staging
     buf = torch.empty((n, ld), dtype=torch.float64, device=dev)
     sq = torch.empty(n, dtype=torch.float64, device=dev)
     mode = {'euclidean': 0, 'correlation': 1}[metric]

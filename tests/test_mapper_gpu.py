@@ -34,8 +34,22 @@ def _bits(a):
     return numpy.ascontiguousarray(a, dtype=numpy.float64).view(numpy.int64)
 
 
-@pytest.mark.parametrize('shape', [(70, 37), (300, 200), (129, 16), (5, 1001)])
-def test_row_normalize_and_gram_bit_exact(shape):
+@pytest.mark.parametrize('shape', [(70, 37), (300, 200), (129, 16), (5, 1001), (260, 50), (150, 64)])
+@pytest.mark.parametrize('bulk', ['0', '1'])
+def test_row_normalize_and_gram_bit_exact(shape, bulk, monkeypatch):
+    import subprocess
+    import sys
+    if bulk == '1':
+        # the TMA bulk-copy staging is selected once per process: run this case in a child process
+        code = ("import os, sys, importlib.util; os.environ['SCTDA_GEMM_TMA_BULK'] = '1'; sys.path.insert(0, %r); "
+                "spec = importlib.util.spec_from_file_location('tm', %r); m = importlib.util.module_from_spec(spec); "
+                "spec.loader.exec_module(m); m.test_row_normalize_and_gram_bit_exact(%r, '0', None)"
+                % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.abspath(__file__), shape))
+        if not torch.cuda.is_available():
+            pytest.skip('no CUDA device')
+        r = subprocess.run([sys.executable, '-c', code], stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+        assert r.returncode == 0, r.stdout.decode()[-2000:]
+        return
     from oracle import mapper_oracle as mo
     from sctda_b200 import mapper
     ctx = _gpu()
@@ -55,6 +69,10 @@ def test_row_normalize_and_gram_bit_exact(shape):
         G_ref = mo.gram(Xn_ref, ra, rb)
         numpy.testing.assert_allclose(G, G_ref, rtol=1e-13, atol=1e-13)
         assert (_bits(G) == _bits(G_ref)).all(), 'DMMA result is not the sequential fma chain'
+        if g % 2 == 0:
+            # rows without zero padding to a multiple of 16 columns (always the cp.async staging)
+            G2 = mapper.gram_gather(ctx, Xn.contiguous(), ra, rb).cpu().numpy()
+            assert (_bits(G2) == _bits(G_ref)).all()
 
 
 @pytest.mark.parametrize('metric', ['euclidean', 'correlation'])
