@@ -267,6 +267,12 @@ int32_t sctda_root_scores(sctda_ctx* ctx, int32_t V, const int32_t* d_adj_off, c
  */
 int32_t sctda_selftest_div(sctda_ctx* ctx, int64_t n_trials, int64_t* out_mismatches);
 
+/* Diagnostic: the permutation kernel's own log1p (positive finite arguments) against the generic
+ * CUDA log1p over n_trials pseudo-random arguments in 2^-60 .. 2^40: returns the largest
+ * difference in units of the last place (both are sub-ulp accurate: expected <= 2).
+ * Synchronises the host. */
+int32_t sctda_selftest_log1p(sctda_ctx* ctx, int64_t n_trials, int64_t* out_max_ulp);
+
 #ifdef __cplusplus
 }
 #endif

@@ -58,6 +58,7 @@ SIGNATURES = {
     'sctda_root_scores': (c_i32, [c_ptr, c_i32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     'sctda_selftest_div': (c_i32, [c_ptr, c_i64, ctypes.POINTER(c_i64)]),
     'sctda_probe_l2_read_gbs': (c_i32, [c_ptr, ctypes.POINTER(c_f64)]),
+    'sctda_selftest_log1p': (c_i32, [c_ptr, c_i64, ctypes.POINTER(c_i64)]),
     'sctda_node_stats': (c_i32, [c_ptr, ctypes.POINTER(Graph), c_i32, c_ptr, c_i64, c_i32, c_ptr,
                                  c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     'sctda_conn_perm_test': (c_i32, [c_ptr, ctypes.POINTER(Graph), c_i32, c_ptr, c_i64, c_i32,

@@ -225,14 +225,61 @@ __global__ void inv_size_kernel(const int32_t* __restrict__ off, int V, double* 
     if (k < V) inv_q[k] = 1.0 / (double)(off[k + 1] - off[k]);
 }
 
+// log1p(x) for finite x > 0, error below 1 ulp (the accuracy class of the libm numexpr / numpy call at
+// ref:983), without the special-case and slow paths of the generic routine: the node loop calls it
+// V times per gene and permutation, and the generic log1p made the node epilogue ~250 instructions.
+// Method (the classical one): 1 + x = 2^k * (1 + f) with 1 + f in [sqrt(2)/2, sqrt(2)), the rounding
+// error of 1 + x carried as c; s = f / (2 + f), log(1 + f) = f - f^2/2 + s * (f^2/2 + R(s^2)) with a
+// degree-7 minimax polynomial R; the quotient by a Newton-refined approximate reciprocal.
+// (Measured: -25 % executed instructions, no change in throughput — the kernel is bound by the
+// gather, not by issue.)
+__device__ __forceinline__ double log1p_pos(double x) {
+    const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10;
+    const double Lp1 = 6.666666666666735130e-01, Lp2 = 3.999999999940941908e-01, Lp3 = 2.857142874366239149e-01,
+                 Lp4 = 2.222219843214978396e-01, Lp5 = 1.818357216161805012e-01, Lp6 = 1.531383769920937332e-01,
+                 Lp7 = 1.479819860511658591e-01;
+    double f = x, c = 0.0;
+    int k = 0;
+    if (!(x < 0.41421356237309503)) {
+        const double u = 1.0 + x;
+        int hu = __double2hiint(u);
+        k = (hu >> 20) - 1023;
+        c = (k > 0) ? 1.0 - (u - x) : x - (u - 1.0);            // rounding error of 1 + x
+        double ru;
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(ru) : "d"(u));   // c / u only needs ~20 bits
+        c *= ru;
+        hu &= 0x000fffff;
+        double un;
+        if (hu < 0x6a09e) un = __hiloint2double(hu | 0x3ff00000, __double2loint(u));
+        else { k += 1; un = __hiloint2double(hu | 0x3fe00000, __double2loint(u)); }
+        f = un - 1.0;
+    }
+    const double hfsq = 0.5 * f * f;
+    const double d = 2.0 + f;
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    double e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+    double s = f * r;
+    s = fma(fma(-d, s, f), r, s);                                // s = f / (2 + f)
+    const double z = s * s;
+    const double R = z * fma(z, fma(z, fma(z, fma(z, fma(z, fma(z, Lp7, Lp6), Lp5), Lp4), Lp3), Lp2), Lp1);
+    if (k == 0) return f - (hfsq - s * (hfsq + R));
+    const double dk = (double)k;
+    return dk * ln2_hi - ((hfsq - (s * (hfsq + R) + (dk * ln2_lo + c))) - f);
+}
+
 // float32(log1p(t1) / 0.693147) for t1 >= 0 (ref:983 and the float32 array of ref:972).
 __device__ __forceinline__ float pm_log2_value(double t1) {
     const double c = 0.693147;
     const double rc = 1.0 / 0.693147;                 // RN(1/c), folded at compile time
-    const bool zero = !(t1 > 0.0);
-    double l = log1p(zero ? 1.0 : t1);               // keep every lane on log1p's fast path
-    float r = (float)div_rn(l, c, rc);
-    return zero ? (float)t1 : r;                      // t1 == 0 -> 0; NaN propagates
+    const bool ok = t1 > 0.0 && t1 < 1e300;
+    const float r = (float)div_rn(log1p_pos(ok ? t1 : 1.0), c, rc);
+    // t1 == 0 -> 0, NaN -> NaN, +inf -> +inf: all equal to float(t1); nothing else reaches here
+    // (a finite sum of 2^x - 1 above 1e300 would need x > 996)
+    return ok ? r : (float)t1;
 }
 
 struct PermArgs {
@@ -531,6 +578,20 @@ __global__ void selftest_div_kernel(int64_t n, uint64_t seed, unsigned long long
     if (bad) atomicAdd(mismatches, 1ull);
 }
 
+// log1p_pos against the generic log1p: largest difference in units of the last place
+__global__ void selftest_log1p_kernel(int64_t n, uint64_t seed, unsigned long long* max_ulp) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t x = seed + 0x9E3779B97F4A7C15ull * (uint64_t)(i + 1);
+    x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 27; x *= 0x94D049BB133111EBull; x ^= x >> 31;
+    const uint64_t mant = x & 0xFFFFFFFFFFFFFull;
+    const int ex = (int)((x >> 52) % 100) - 60;                  // 2^-60 .. 2^39
+    const double v = __longlong_as_double((long long)(((uint64_t)(1023 + ex) << 52) | mant));
+    const long long a = __double_as_longlong(log1p_pos(v)), b = __double_as_longlong(log1p(v));
+    const unsigned long long d = (unsigned long long)(a > b ? a - b : b - a);
+    atomicMax(max_ulp, d);
+}
+
 int check_graph(sctda_ctx* ctx, const sctda_graph* gr) {
     if (!gr) return sctda_fail(ctx, SCTDA_ERR_INVALID, "graph is NULL%s");
     if (gr->V < 2) return sctda_fail(ctx, SCTDA_ERR_INVALID, "graph needs V >= 2 nodes (V/(V-1) factor, ref:989)%s");
@@ -674,5 +735,21 @@ extern "C" int32_t sctda_selftest_div(sctda_ctx* ctx, int64_t n_trials, int64_t*
     unsigned long long h = 0;
     SCTDA_CUDA(ctx, cudaMemcpy(&h, d, sizeof(h), cudaMemcpyDeviceToHost));
     *out_mismatches = (int64_t)h;
+    return SCTDA_OK;
+}
+
+extern "C" int32_t sctda_selftest_log1p(sctda_ctx* ctx, int64_t n_trials, int64_t* out_max_ulp) {
+    if (!ctx || !out_max_ulp || n_trials < 0) return SCTDA_ERR_INVALID;
+    SCTDA_CUDA(ctx, cudaSetDevice(ctx->device));
+    unsigned long long* d = (unsigned long long*)sctda_ws(ctx, WS_MISC, 256);
+    if (!d) return SCTDA_ERR_NOMEM;
+    SCTDA_CUDA(ctx, cudaMemset(d, 0, sizeof(unsigned long long)));
+    if (n_trials > 0) {
+        selftest_log1p_kernel<<<(unsigned)cdiv64(n_trials, 256), 256>>>(n_trials, 0x10961ull, d);
+        SCTDA_LAUNCH_CHECK(ctx, "selftest_log1p_kernel");
+    }
+    unsigned long long h = 0;
+    SCTDA_CUDA(ctx, cudaMemcpy(&h, d, sizeof(h), cudaMemcpyDeviceToHost));
+    *out_max_ulp = (int64_t)h;
     return SCTDA_OK;
 }

@@ -50,12 +50,34 @@ def _to_float_column(strings):
     return out, ok
 
 
-def read_table(path, shift=None, csv=False):
+def write_table_sidecar(path, names, Y, cell_id=(), libs=(), cdr=None):
+    """Binary side-car `<table>.npz` of an expression table: the TSV stays the
+    interchange format of the reference; when the side-car is present and newer than the TSV,
+    read_table loads it instead of parsing 10^8-10^9 text fields in Python."""
+    numpy.savez(path + '.npz', names=numpy.array(list(names), dtype=object), Y=numpy.asarray(Y, dtype=numpy.float64),
+                cell_id=numpy.array(list(cell_id), dtype=object), libs=numpy.array(list(libs), dtype=object),
+                cdr=numpy.zeros(0) if cdr is None else numpy.asarray(cdr, dtype=numpy.float64))
+
+
+def _read_sidecar(path):
+    import os
+    side = path + '.npz'
+    if not os.path.exists(side) or os.path.getmtime(side) < os.path.getmtime(path):
+        return None
+    z = numpy.load(side, allow_pickle=True)
+    return list(z['names']), numpy.ascontiguousarray(z['Y']), list(z['cell_id']), list(z['libs']), z['cdr']
+
+
+def read_table(path, shift=None, csv=False, sidecar=True):
     """ref:835-885.  Returns (names, Y, cell_id, libs, cdr):
     names   column names that become keys of dicgenes (header order),
     Y       float64 [len(names), Ncells], gene-major (one row per column of the file),
     cell_id / libs  the non-numeric fields of column 0 / column 'lib' (shift=None only),
     cdr     fraction of columns with value > 0 per cell, excluding ID / lib / timepoint."""
+    if sidecar and shift is None:
+        got = _read_sidecar(path)
+        if got is not None:
+            return got
     sep = ',' if csv else '\t'
     with open(path, 'r') as f:
         lines = f.read().split('\n')

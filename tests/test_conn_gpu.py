@@ -294,3 +294,12 @@ def test_reciprocal_division_is_ieee_division():
     bad = ctypes.c_int64(-1)
     ctx.check(ctx.lib.sctda_selftest_div(ctx.handle, 1 << 26, ctypes.byref(bad)))
     assert bad.value == 0
+
+
+def test_own_log1p_is_sub_ulp():
+    """log1p_pos (argument reduction + degree-7 minimax series) against CUDA's log1p."""
+    ctx = _gpu()
+    import ctypes
+    d = ctypes.c_int64(-1)
+    ctx.check(ctx.lib.sctda_selftest_log1p(ctx.handle, 1 << 26, ctypes.byref(d)))
+    assert 0 <= d.value <= 2          # two sub-ulp results differ by at most 2 units in the last place

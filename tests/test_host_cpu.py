@@ -108,6 +108,22 @@ def test_read_table_matches_oracle_parse(golden_dir, name):
     assert n4 == [names[3], names[5]]
 
 
+def test_table_sidecar_round_trip(golden_dir, tmp_path):
+    import shutil
+    from sctda_b200 import formats
+    path = str(tmp_path / 't.all.tsv')
+    shutil.copy(os.path.join(golden_dir, 'unrooted_a.all.tsv'), path)
+    names, Y, cell_id, libs, cdr = formats.read_table(path)
+    formats.write_table_sidecar(path, names, Y, cell_id, libs, cdr)
+    n2, Y2, c2, l2, cdr2 = formats.read_table(path)
+    assert n2 == names and list(c2) == list(cell_id) and list(l2) == list(libs)
+    numpy.testing.assert_array_equal(Y2, Y)
+    numpy.testing.assert_array_equal(cdr2, cdr)
+    # a TSV newer than its side-car wins
+    os.utime(path + '.npz', (1, 1))
+    assert formats._read_sidecar(path) is None
+
+
 def test_py2_str_and_writers(tmp_path):
     from sctda_b200 import formats
     for v in (0.0, 0.904, 0.02489375434321234, 710, 1e-20, 3.0, None, 1e16, 123456789012.0, float('nan')):
