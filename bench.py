@@ -269,8 +269,8 @@ def run_mapper(a, ctx, dev, steps, warmup, rank=0, world=1):
                       'cover_multiplicity': float(prof['Mtot']) / N, 'nodes': prof['V'], 'edges': prof['E'],
                       'largest_patch': int(m.max()), 'sum_m2': sum_m2},
            'stages_ms': {k[:-3]: round(float(v), 3) for k, v in prof.items()
-                         if k.endswith('_ms') and k not in ('total_ms', 'gemm_ms')},
-           'pca_lens_ms_untimed': lens_ms,
+                         if k.endswith('_ms') and k not in ('total_ms', 'gemm_ms', 'host_ms') and isinstance(v, (int, float))},
+           'pca_lens_ms_untimed': lens_ms, 'host_ms': prof.get('host_ms'),
            'roofline': {'bound': 'tensor', 'achieved': flops / (gms * 1e-3) / 1e12, 'peak': peak, 'unit': 'TFLOP/s',
                         'frac': flops / (gms * 1e-3) / 1e12 / peak, 'traffic': None, 'kernel': 'gemm_kernel (FP64 DMMA)',
                         'kernel_ms': gms, 'flops': flops,

@@ -247,13 +247,22 @@ def build_graph_distributed(ctx, Xd, lens, resolution, gain, equalize=True, max_
     res.bin_off = torch.empty(B + 1, dtype=torch.int32, device=dev)
     ctx.check(ctx.lib.sctda_cover_count(ctx.handle, N, _lib.ptr(lens_d), 2, r, _lib.ptr(b[0]), _lib.ptr(b[1]),
                                         _lib.ptr(b[2]), _lib.ptr(b[3]), _lib.ptr(res.bin_off), st))
+    import time as _time
     bin_off = res.bin_off.cpu().numpy()
+    _t = [_time.perf_counter()]
     mtot = int(bin_off[B])
     _b_members = _Buf(mtot, torch.int32, dev)
     res.members = _b_members.view
     ctx.check(ctx.lib.sctda_cover_fill(ctx.handle, N, r, _lib.ptr(res.bin_off), _b_members.ptr, st))
-    labels, bin_K = parallel.patch_sharded_labels(bin_off, res.members.cpu().numpy(),
-                                                  lambda so, sm: cluster_sub_csr(ctx, Xn, so, sm, max_K))
+    members_h = res.members.cpu().numpy()
+    _t.append(_time.perf_counter())
+
+    def _compute(so, sm):
+        out = cluster_sub_csr(ctx, Xn, so, sm, max_K)
+        _t.append(_time.perf_counter())
+        return out
+    labels, bin_K = parallel.patch_sharded_labels(bin_off, members_h, _compute)
+    _t.append(_time.perf_counter())
     res.labels = torch.as_tensor(labels).to(dev)
     res.bin_K = torch.as_tensor(bin_K).to(dev)
     res.bin_db = None
@@ -261,7 +270,10 @@ def build_graph_distributed(ctx, Xd, lens, resolution, gain, equalize=True, max_
     if profile is not None:
         e1.record(torch.cuda.current_stream(dev))
         torch.cuda.current_stream(dev).synchronize()
-        profile.update({'total_ms': e0.elapsed_time(e1), 'Mtot': mtot, 'V': res.V, 'E': res.E,
+        _t.append(_time.perf_counter())
+        profile.update({'host_ms': {'cover_to_host': 1e3 * (_t[1] - _t[0]), 'cluster_shard': 1e3 * (_t[2] - _t[1]),
+                                    'exchange_and_merge': 1e3 * (_t[3] - _t[2]), 'nodes_nerve': 1e3 * (_t[4] - _t[3])},
+                        'total_ms': e0.elapsed_time(e1), 'Mtot': mtot, 'V': res.V, 'E': res.E,
                         'gemm_ms': ctx.last_kernel_ms() if ctx.timing_enabled else None})
     return res
 
