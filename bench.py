@@ -411,11 +411,13 @@ def run_own(a):
     bytes_per_unit = 4.0 * a.cells + 8.0 * a.cells / a.perms
     k_ms = float(numpy.mean(kernel_ms))
     achieved = bytes_per_unit * G * a.perms / (k_ms * 1e-3) / 1e9
-    traffic = None
+    traffic = None                                               # DRAM bytes of this launch, from the committed ncu capture
     tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
     if os.path.exists(tpath):
         with open(tpath) as f:
-            traffic = json.load(f).get('conn_perm_kernel_bytes_per_launch')
+            per_unit = json.load(f).get('conn_perm_kernel_dram_bytes_per_gene_perm')
+        if per_unit:
+            traffic = per_unit * G * a.perms
     # on-chip view: with the permutation block shared, every gene*perm gathers 8*Mtot bytes of table
     # rows from L2 plus the float32 node values of the sparse product (model, matches ncu's
     # l1tex__m_xbar2l1tex_read_bytes to a few per cent); ceiling = measured L2 -> SM read bandwidth
@@ -423,7 +425,8 @@ def run_own(a):
     l2_peak = ctx.probe_l2_read_gbs()
     l2_ach = l2_bytes_per_unit * G * a.perms / (k_ms * 1e-3) / 1e9
     roof = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-            'traffic': traffic, 'kernel': 'conn_perm_kernel', 'kernel_ms': k_ms, 'peak_source': peak_src,
+            'traffic': traffic, 'traffic_note': 'bytes per launch = ncu dram__bytes_read+write per gene*perm (profiles/traffic.json) x units of this launch; algorithmic bytes per launch = algorithmic_bytes_per_unit x units',
+            'kernel': 'conn_perm_kernel', 'kernel_ms': k_ms, 'peak_source': peak_src,
             'algorithmic_bytes_per_unit': bytes_per_unit,
             'onchip': {'bound': 'l2', 'achieved': l2_ach, 'peak': l2_peak, 'unit': 'GB/s', 'frac': l2_ach / l2_peak,
                        'bytes_per_unit': l2_bytes_per_unit, 'peak_source': 'sctda_probe_l2_read_gbs in this run'},
