@@ -315,3 +315,18 @@ def test_every_mst_kernel_gives_the_same_graph(monkeypatch):
         assert res.V == len(clusters)
         assert all(list(mem[off[k]:off[k + 1]]) == list(c) for k, c in enumerate(clusters)), thr
         assert [tuple(e) for e in res.edges.cpu().numpy().tolist()] == edges
+
+
+def test_distributed_build_equals_single_device_build():
+    """build_graph_distributed with a single rank (no process group) walks the sharded code path
+    (LPT assignment, sub-CSR, label exchange) and must give the graph of build_graph_device."""
+    ctx = _gpu()
+    from sctda_b200 import mapper
+    X, lens = _data(1500, 64, seed=12)
+    dev = torch.device('cuda', 0)
+    Xd = mapper._padded_device_table(X, dev)
+    a = mapper.build_graph_device(ctx, Xd, lens, 6, 0.7)
+    b = mapper.build_graph_distributed(ctx, Xd, lens, 6, 0.7)
+    assert a.V == b.V and a.E == b.E
+    for name in ('bin_off', 'members', 'labels', 'bin_K', 'node_off', 'node_members', 'node_bin', 'edges'):
+        assert torch.equal(getattr(a, name), getattr(b, name)), name
