@@ -198,6 +198,14 @@ int32_t sctda_pairdist_rows_f64(sctda_ctx* ctx, int32_t N, int32_t G, const doub
                                 const double* d_sq, int32_t r0, int32_t r1, int32_t metric,
                                 double* d_D, int64_t ldd, void* stream);
 
+/* One SMACOF pass of the MDS lens (apply_lens(lens='mds'), the reference's default lens; sklearn.manifold
+ * MDS, metric variant): for the configuration d_Z [N, 2] and the dissimilarities d_D [N, ldd]
+ * (sctda_pairdist_rows_f64), writes the Guttman transform d_Znew [N, 2] and d_stats[0] = stress(Z) =
+ * sum_ij (|z_i - z_j| - delta_ij)^2 / 2, d_stats[1] = sum_ij |z_i - z_j|^2.  The iteration, the
+ * convergence test and the restarts are driven by the host (sctda_b200.mapper.smacof_device). */
+int32_t sctda_smacof_pass(sctda_ctx* ctx, int32_t N, const double* d_D, int64_t ldd, const double* d_Z,
+                          double* d_Znew, double* d_stats, void* stream);
+
 /* Cover (mapper_graph stage 1).  d_lens [N, ldl>=2]: the 2-D lens.  d_lo0, d_hi0, d_lo1, d_hi1 [r]: open interval
  * bounds per axis (fenceposts widened by gain; the host computes them from percentiles).
  * Patch b = i*r + j holds the cells with lo0[i] < lens0 < hi0[i] and lo1[j] < lens1 < hi1[j].

@@ -89,6 +89,47 @@ def pairwise_distances(ctx, Xd, metric, row_block=8192):
     return D
 
 
+def smacof_device(ctx, D, n_components=2, init=None, n_init=1, max_iter=300, eps=1e-6, random_state=None,
+                  return_n_iter=False):
+    """Metric MDS by SMACOF on a device dissimilarity matrix D [N, N] (symmetric, float64), following
+    sklearn.manifold.smacof / _smacof_single step by step: uniform random start from `random_state`
+    (or `init`), Guttman transform, stress of the new configuration, stop when
+    (old_stress - stress) / (sum of squared distances / 2) < eps, best of n_init restarts.
+    Every iteration is one sctda_smacof_pass over D; returns (positions [N, 2] device tensor, stress)."""
+    import sklearn.utils
+    if n_components != 2:
+        raise ValueError('the lens is two-dimensional')
+    dev = D.device
+    n = int(D.shape[0])
+    rs = sklearn.utils.check_random_state(random_state)
+    if init is not None:
+        n_init = 1
+    stats = torch.zeros(2, dtype=torch.float64, device=dev)
+    best = None
+    for _ in range(int(n_init)):
+        X0 = numpy.asarray(init, dtype=numpy.float64) if init is not None else rs.uniform(size=n * 2).reshape((n, 2))
+        cur = torch.from_numpy(numpy.ascontiguousarray(X0)).to(dev)
+        nxt = torch.empty_like(cur)
+        old = None
+        n_iter = 0
+        # pass p on X_p yields stress(X_p) and X_{p+1}; sklearn's iteration it produces X_{it+1} and tests its stress
+        for p in range(int(max_iter) + 1):
+            ctx.check(ctx.lib.sctda_smacof_pass(ctx.handle, n, _lib.ptr(D), int(D.stride(0)), _lib.ptr(cur), _lib.ptr(nxt),
+                                                _lib.ptr(stats), _stream(dev)))
+            if p >= 1:
+                stress, ssd = [float(v) for v in stats.cpu()]
+                n_iter = p
+                if old is not None and (old - stress) / (ssd / 2.0) < eps:
+                    break
+                old = stress
+                if p == int(max_iter):
+                    break
+            cur, nxt = nxt, cur
+        if best is None or stress < best[1]:
+            best = (cur.clone(), stress, n_iter)
+    return (best[0], best[1], best[2]) if return_n_iter else (best[0], best[1])
+
+
 def gram_gather(ctx, Xn, rows_a, rows_b):
     dev = Xn.device
     ra = torch.as_tensor(rows_a, dtype=torch.int32, device=dev).contiguous()
@@ -316,8 +357,9 @@ def apply_lens(df, lens='pca', metric='correlation', dissimilarity=None, device=
     """sakmapper.apply_lens as called at ref:745-753.  Returns a DataFrame (N x 2, index of df).
     'pca': the two leading principal components, computed on the device (sklearn.decomposition.PCA
     sign convention); 'mds': the dissimilarity matrix in `metric` is computed on the device
-    (sctda_pairdist_rows_f64) and embedded by sklearn.manifold.MDS on the host (SMACOF is a
-    SURVEY.md §8f 'next' row); dissimilarity='precomputed' takes df itself as the matrix;
+    (sctda_pairdist_rows_f64) and embedded on the device by SMACOF (smacof_device: sklearn.manifold.MDS's
+    algorithm and keyword arguments n_init / max_iter / eps / random_state / init);
+    dissimilarity='precomputed' takes df itself as the matrix;
     'neighbor': sklearn.manifold.SpectralEmbedding on the host."""
     import pandas
     X = numpy.asarray(_values(df), dtype=numpy.float64)
@@ -329,19 +371,16 @@ def apply_lens(df, lens='pca', metric='correlation', dissimilarity=None, device=
         Xd = torch.from_numpy(numpy.ascontiguousarray(X)).to(dev)
         out = pca_lens_device(Xd).cpu().numpy()
     elif lens == 'mds':
-        import sklearn.manifold
+        ctx = _lib.context(device)
         if dissimilarity == 'precomputed':
-            D = X
+            D = torch.from_numpy(numpy.ascontiguousarray(0.5 * (X + X.T))).to(dev)      # sklearn's check_symmetric
         else:
-            ctx = _lib.context(device)
-            D = pairwise_distances(ctx, _padded_device_table(X, dev), metric).cpu().numpy()
-            D = 0.5 * (D + D.T)
-        kw = dict(kwargs)
-        kw.setdefault('n_components', 2)
-        try:
-            out = sklearn.manifold.MDS(dissimilarity='precomputed', **kw).fit_transform(D)
-        except TypeError:
-            out = sklearn.manifold.MDS(metric='precomputed', **kw).fit_transform(D)
+            D = pairwise_distances(ctx, _padded_device_table(X, dev), metric)
+        kw = {k: kwargs[k] for k in ('n_components', 'n_init', 'max_iter', 'eps', 'random_state', 'init') if k in kwargs}
+        unknown = set(kwargs) - set(kw) - {'n_jobs', 'verbose'}
+        if unknown:
+            raise TypeError('apply_lens(lens="mds"): unsupported MDS arguments %s' % sorted(unknown))
+        out = smacof_device(ctx, D, **kw)[0].cpu().numpy()
     elif lens == 'neighbor':
         import sklearn.manifold
         kw = dict(kwargs)

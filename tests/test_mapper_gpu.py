@@ -330,3 +330,37 @@ def test_distributed_build_equals_single_device_build():
     assert a.V == b.V and a.E == b.E
     for name in ('bin_off', 'members', 'labels', 'bin_K', 'node_off', 'node_members', 'node_bin', 'edges'):
         assert torch.equal(getattr(a, name), getattr(b, name)), name
+
+
+def test_smacof_matches_sklearn():
+    """The device SMACOF (one sctda_smacof_pass per iteration) against sklearn.manifold.smacof from the
+    same start: same number of iterations, same stress, same configuration."""
+    import warnings
+    import sklearn.manifold
+    ctx = _gpu()
+    from sctda_b200 import mapper
+    X, _ = _data(300, 60, seed=8)
+    dev = torch.device('cuda', 0)
+    for metric in ('correlation', 'euclidean'):
+        D = mapper.pairwise_distances(ctx, mapper._padded_device_table(X, dev), metric)
+        Dh = D.cpu().numpy()
+        assert (Dh == Dh.T).all()
+        X0 = numpy.random.RandomState(3).uniform(size=(300, 2))
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            ref_pos, ref_stress, ref_it = sklearn.manifold.smacof(Dh, metric=True, n_components=2, init=X0.copy(), n_init=1,
+                                                                  max_iter=300, eps=1e-6, normalized_stress=False,
+                                                                  return_n_iter=True)
+        pos, stress, it = mapper.smacof_device(ctx, D, init=X0.copy(), max_iter=300, eps=1e-6, return_n_iter=True)
+        assert abs(it - ref_it) <= 1
+        assert stress == pytest.approx(ref_stress, rel=1e-6)
+        if it == ref_it:
+            numpy.testing.assert_allclose(pos.cpu().numpy(), ref_pos, rtol=1e-5, atol=1e-7)
+    # random restarts draw their starts from the RandomState exactly as sklearn does
+    pos1, s1 = mapper.smacof_device(ctx, D, n_init=2, max_iter=40, random_state=5)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        ref_pos, ref_s = sklearn.manifold.smacof(Dh, metric=True, n_components=2, n_init=2, max_iter=40, eps=1e-6, random_state=5,
+                                                 normalized_stress=False)
+    assert s1 == pytest.approx(ref_s, rel=1e-6)
+    numpy.testing.assert_allclose(pos1.cpu().numpy(), ref_pos, rtol=1e-5, atol=1e-7)
