@@ -141,7 +141,7 @@ def gram_gather(ctx, Xn, rows_a, rows_b):
 
 
 # ----------------------------------------------------------------------------------------------
-# cover bounds (host: 2(r+1) order statistics of the lens)
+# cover bounds: 2(r+1) order statistics of the lens (host reference form and device form)
 # ----------------------------------------------------------------------------------------------
 def cover_bounds(lens, resolution, gain, equalize=True):
     """Open interval bounds per axis: fenceposts = numpy.percentile(axis, k*100/r) (equalize) or
@@ -158,6 +158,42 @@ def cover_bounds(lens, resolution, gain, equalize=True):
             posts = numpy.linspace(v.min(), v.max(), r + 1)
         w = posts[1:] - posts[:-1]
         out += [posts[:-1] - (0.5 * gain) * w, posts[1:] + (0.5 * gain) * w]
+    return out
+
+
+def cover_bounds_device(lens_d, resolution, gain, equalize=True):
+    """cover_bounds on the device, without a host round trip: torch.sort (library plumbing) for the
+    order statistics, then numpy.percentile's 'linear' rule operation by operation in float64
+    ((n-1)*q, floor, gamma, a + (b-a)*gamma, switched to b - (b-a)*(1-gamma) for gamma >= 0.5), so the
+    fenceposts are the bits numpy produces (the GPU parity tests compare the patches exactly)."""
+    r = int(resolution)
+    dev = lens_d.device
+    n = int(lens_d.shape[0])
+    out = []
+    k = torch.arange(r + 1, dtype=torch.float64, device=dev)
+    for ax in (0, 1):
+        v = lens_d[:, ax].contiguous()
+        if equalize:
+            srt = torch.sort(v).values
+            q = ((k * 100.0) / float(r)) / 100.0
+            virt = float(n - 1) * q
+            prev = torch.floor(virt)
+            above = virt >= float(n - 1)
+            pi = torch.where(above, torch.full_like(prev, n - 1), prev).to(torch.int64).clamp_(0, n - 1)
+            ni = torch.where(above, torch.full_like(prev, n - 1), prev + 1).to(torch.int64).clamp_(0, n - 1)
+            gamma = virt - torch.where(above, torch.full_like(prev, -1.0), prev)
+            a, b = srt[pi], srt[ni]
+            diff = b - a
+            lo_half = a + diff * gamma
+            hi_half = b - diff * (1.0 - gamma)
+            posts = torch.where(gamma >= 0.5, hi_half, lo_half)
+        else:
+            start, stop = v.min(), v.max()
+            step = (stop - start) / float(r)
+            posts = k * step + start                       # numpy.linspace: arange * step + start, last = stop
+            posts[r] = stop
+        w = posts[1:] - posts[:-1]
+        out += [(posts[:-1] - (0.5 * gain) * w).contiguous(), (posts[1:] + (0.5 * gain) * w).contiguous()]
     return out
 
 
@@ -179,9 +215,6 @@ def build_graph_device(ctx, Xd, lens, resolution, gain, equalize=True, stat='db'
     if not isinstance(lens, torch.Tensor):
         lens = numpy.array(lens, dtype=numpy.float64)
     lens_d = torch.as_tensor(lens, dtype=torch.float64).to(dev).contiguous()
-    if bounds is None:
-        bounds = cover_bounds(lens_d.cpu().numpy(), r, gain, equalize)
-    b = [torch.from_numpy(numpy.ascontiguousarray(x)).to(dev) for x in bounds]
     st = _stream(dev)
     marks = []
 
@@ -191,6 +224,11 @@ def build_graph_device(ctx, Xd, lens, resolution, gain, equalize=True, stat='db'
             e.record(torch.cuda.current_stream(dev))
             marks.append((name, e))
     mark('start')
+    if bounds is None:
+        b = cover_bounds_device(lens_d, r, gain, equalize)
+    else:
+        b = [torch.from_numpy(numpy.ascontiguousarray(x)).to(dev) for x in bounds]
+    mark('bounds')
     Xn, _ = row_normalize(ctx, Xd, metric)
     mark('normalize')
     res = MapperDeviceResult()
@@ -275,13 +313,14 @@ def build_graph_distributed(ctx, Xd, lens, resolution, gain, equalize=True, max_
     N, G = Xd.shape
     r = int(resolution)
     B = r * r
-    lens_h = lens.cpu().numpy() if isinstance(lens, torch.Tensor) else numpy.array(lens, dtype=numpy.float64)
-    lens_d = torch.as_tensor(lens_h, dtype=torch.float64).to(dev).contiguous()
-    b = [torch.from_numpy(numpy.ascontiguousarray(x)).to(dev) for x in cover_bounds(lens_h, r, gain, equalize)]
+    if not isinstance(lens, torch.Tensor):
+        lens = numpy.array(lens, dtype=numpy.float64)
+    lens_d = torch.as_tensor(lens, dtype=torch.float64).to(dev).contiguous()
     st = _stream(dev)
     if profile is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(torch.cuda.current_stream(dev))
+    b = cover_bounds_device(lens_d, r, gain, equalize)
     Xn, _ = row_normalize(ctx, Xd, metric)
     res = MapperDeviceResult()
     res.r = r

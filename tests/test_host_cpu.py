@@ -138,3 +138,24 @@ def test_py2_str_and_writers(tmp_path):
     formats.write_mapper_json(p + '.json', [[3, 1], numpy.array([2])])
     with open(p + '.json') as f:
         assert json.load(f) == {'0': [3, 1], '1': [2]}
+
+
+def test_cover_bounds_device_form_is_numpy_percentile():
+    """The torch form of the cover fenceposts (used on the device) against numpy.percentile / linspace,
+    bit for bit (run here on CPU tensors; the GPU parity tests compare the resulting patches)."""
+    import torch
+    from oracle import mapper_oracle as mo
+    from sctda_b200 import mapper
+    rng = numpy.random.RandomState(0)
+    for n in (7, 100, 1001):
+        lens = rng.normal(size=(n, 2))
+        lens[3] = lens[4]
+        for r in (1, 5, 20, 30):
+            for eq in (True, False):
+                for gain in (0.4, 3.0):
+                    d = mapper.cover_bounds_device(torch.from_numpy(lens), r, gain, eq)
+                    h = mapper.cover_bounds(lens, r, gain, eq)
+                    for a, b in zip(d, h):
+                        assert (a.numpy().view(numpy.int64) == numpy.ascontiguousarray(b).view(numpy.int64)).all()
+                    lo0, hi0 = mo.intervals(mo.fenceposts(lens[:, 0], r, eq), gain)
+                    assert (d[0].numpy() == lo0).all() and (d[1].numpy() == hi0).all()
