@@ -245,6 +245,17 @@ int32_t sctda_nerve_count(sctda_ctx* ctx, int32_t N, int32_t V, const int32_t* d
                           const int32_t* d_node_members, int64_t Mtot, int64_t* d_edge_count, void* stream);
 int32_t sctda_nerve_fill(sctda_ctx* ctx, int32_t V, int32_t* d_edges, void* stream);
 
+/* ---- gene x gene matrices over the nodes ---------------------------------- */
+/*
+ * UnrootedGraph.JSD_matrix (ref:1111-1155): Jensen-Shannon distance between the normalised node
+ * profiles d_P [g, ldp>=V] (sctda_node_stats d_p) of g genes; d_out [g, ldo>=g].
+ * jsd = sqrt(0.5*(h_i + h_j - 2*sum_k f((p_ik+p_jk)/2))), f(x) = x*log2(x), f(0) = 0; no clamping, as
+ * the reference.  (cor_matrix, ref:1157-1163, is sctda_pairdist_rows_f64 on the genes' table rows;
+ * adjacency_matrix, ref:1165-1190, is sctda_gram_gather_f64 on [P; P*A].)
+ */
+int32_t sctda_jsd_matrix(sctda_ctx* ctx, int32_t g, int32_t V, const double* d_P, int64_t ldp, double* d_out,
+                         int64_t ldo, void* stream);
+
 /*
  * HOST function (no GPU work): the permutation source of ref:975-976.  Fills out[rows, S] with
  * arange(S) shuffled row after row exactly as numpy.random.shuffle does on the legacy MT19937

@@ -330,6 +330,45 @@ def centroid(st, genin, ignore_log=False):
     return [None, None]
 
 
+# ----------------------------------------------------------------------------------------------
+# gene x gene matrices (ref:1111-1190)
+# ----------------------------------------------------------------------------------------------
+def jsd_matrix(st, lista):
+    """ref:1117-1155 (the un-chunked branch; the chunked one computes the same numbers)."""
+    ge = numpy.array([[get_gene(st, g)[0][k] for k in st.pl] for g in lista])
+    ge2 = numpy.copy(ge)
+    ge2[ge2 == 0] = 1
+    plogp = numpy.sum(ge2 * numpy.log2(ge2), axis=1)
+    plogptile = numpy.tile(plogp, (len(lista), 1))
+    ge_tile = numpy.tile(ge, (len(lista), 1, 1))
+    ge_tile_T = numpy.transpose(ge_tile, [1, 0, 2])
+    pq = 0.5 * (ge_tile + ge_tile_T)
+    pq[pq == 0] = 1
+    pqlogpq = numpy.sum(pq * numpy.log2(pq), axis=2)
+    jsdiv = 0.5 * (plogptile + plogptile.T - 2 * pqlogpq)
+    with numpy.errstate(invalid='ignore'):
+        return numpy.sqrt(jsdiv), jsdiv
+
+
+def cor_matrix(st, lista):
+    """ref:1157-1163."""
+    import sklearn.metrics.pairwise
+    geys = numpy.array([st.dicgenes[m] for m in lista])
+    return sklearn.metrics.pairwise.pairwise_distances(geys, metric='correlation')
+
+
+def adjacency_matrix(st, lista, ind=1):
+    """ref:1165-1190."""
+    cor = float(len(st.pl)) / float(len(st.pl) - 1)
+    pol = {g: get_gene(st, g)[0] for g in lista}
+    Ai = numpy.linalg.matrix_power(st.adj, ind)
+    mat = []
+    for m1 in lista:
+        ex1 = numpy.array([pol[m1][u] for u in st.pl])
+        mat.append([cor * numpy.dot(numpy.transpose(ex1), numpy.dot(Ai, numpy.array([pol[m2][u] for u in st.pl]))) for m2 in lista])
+    return numpy.array(mat)
+
+
 def py2_str(v):
     """Python-2 `str()` of the values ref:1078-1079 writes: '%.12g' for floats (with a
     trailing '.0' when that prints an integer), plain str for ints / None."""

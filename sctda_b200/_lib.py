@@ -55,6 +55,7 @@ SIGNATURES = {
     'sctda_nodes_fill': (c_i32, [c_ptr, c_i32, c_ptr, c_ptr, c_ptr, c_ptr, c_i32, c_ptr, c_ptr, c_ptr, c_ptr]),
     'sctda_nerve_count': (c_i32, [c_ptr, c_i32, c_i32, c_ptr, c_ptr, c_i64, c_ptr, c_ptr]),
     'sctda_nerve_fill': (c_i32, [c_ptr, c_i32, c_ptr, c_ptr]),
+    'sctda_jsd_matrix': (c_i32, [c_ptr, c_i32, c_i32, c_ptr, c_i64, c_ptr, c_i64, c_ptr]),
     'sctda_mt19937_shuffle_rows': (c_i32, [c_ptr, ctypes.POINTER(c_i32), c_i32, c_i32, c_ptr]),
     'sctda_root_scores': (c_i32, [c_ptr, c_i32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     'sctda_selftest_div': (c_i32, [c_ptr, c_i64, ctypes.POINTER(c_i64)]),

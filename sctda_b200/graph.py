@@ -378,6 +378,44 @@ class UnrootedGraph(object):
                 ties[lo:hi] = ti.cpu().numpy()
         return (list(pvals), ties) if return_ties else list(pvals)
 
+    # -- gene x gene matrices (ref:1111-1190) ---------------------------------------------------------
+    def _profiles(self, lista):
+        """Normalised node profiles P [len(lista), V] of the genes (device), nodes in self.pl order."""
+        Y = self._device_table().index_select(0, self._rows(lista))
+        return node_stats(self._context(), self._device_graph(), Y, log2=self.log2, want_p=True)['p']
+
+    def JSD_matrix(self, lista, maximum_matrix_entries=5 * 10 ** 7, verbose=False):
+        """ref:1111-1155: Jensen-Shannon distance matrix of the genes' node profiles
+        (`maximum_matrix_entries` only bounds the reference's temporaries; accepted and ignored)."""
+        import ctypes
+        ctx = self._context()
+        P = self._profiles(lista)
+        g, V = int(P.shape[0]), int(P.shape[1])
+        out = torch.empty((g, g), dtype=torch.float64, device=P.device)
+        ctx.check(ctx.lib.sctda_jsd_matrix(ctx.handle, g, V, _lib.ptr(P), int(P.stride(0)), _lib.ptr(out), g,
+                                           ctypes.c_void_p(torch.cuda.current_stream(P.device).cuda_stream)))
+        return out.cpu().numpy()
+
+    def cor_matrix(self, lista, c=1):
+        """ref:1157-1163: correlation distance matrix of the genes over the table rows (cells)."""
+        from . import mapper
+        Y = self._device_table().index_select(0, self._rows(lista))
+        return mapper.pairwise_distances(self._context(), mapper._padded_device_table(Y, Y.device), 'correlation').cpu().numpy()
+
+    def adjacency_matrix(self, lista, ind=1, verbose=False):
+        """ref:1165-1190: V/(V-1) * P A^ind P' for the genes' node profiles (one contraction of [P; P A^ind])."""
+        from . import mapper
+        ctx = self._context()
+        P = self._profiles(lista)
+        g, V = int(P.shape[0]), int(P.shape[1])
+        A = self.adj_csr if ind == 1 else (self.adj_csr ** int(ind))
+        PA = torch.from_numpy(numpy.ascontiguousarray((A @ P.cpu().numpy().T).T)).to(P.device)
+        stacked = mapper._padded_device_table(torch.cat([P, PA], dim=0), P.device)
+        rows = numpy.arange(g)
+        M = mapper.gram_gather(ctx, stacked, rows, rows + g)
+        cor = float(V) / float(V - 1)
+        return (cor * M).cpu().numpy()
+
     # -- table (ref:1053-1086) -----------------------------------------------------------------------
     def _table_rows(self, n, filtercells, filterexp, annotation, rooted, perms):
         s = self._all_stats()

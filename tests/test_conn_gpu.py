@@ -303,3 +303,27 @@ def test_own_log1p_is_sub_ulp():
     d = ctypes.c_int64(-1)
     ctx.check(ctx.lib.sctda_selftest_log1p(ctx.handle, 1 << 26, ctypes.byref(d)))
     assert 0 <= d.value <= 2          # two sub-ulp results differ by at most 2 units in the last place
+
+
+def test_gene_gene_matrices(golden_dir, tmp_path):
+    """JSD_matrix / cor_matrix / adjacency_matrix (ref:1111-1190) of the product class against the
+    oracle restatement on a golden graph."""
+    _gpu()
+    from oracle import conn_oracle as co
+    from sctda_b200 import graph
+    for ext in ('.gexf', '.json', '.all.tsv'):
+        shutil.copy(os.path.join(golden_dir, 'unrooted_a' + ext), str(tmp_path / ('unrooted_a' + ext)))
+    prefix = str(tmp_path / 'unrooted_a')
+    c = graph.UnrootedGraph(prefix, prefix + '.all.tsv', groups=False)
+    st = co.load_state(prefix, prefix + '.all.tsv')
+    st.pl = list(c.pl)
+    st.adj = c.adj
+    genes = ['G%03d' % i for i in (0, 3, 4, 5, 7, 8, 9, 10, 11, 12, 13, 20, 21, 22, 23, 6, 14, 15)]
+    jsd, jsdiv = co.jsd_matrix(st, genes)
+    got = c.JSD_matrix(genes)
+    assert got.shape == (len(genes), len(genes)) and (numpy.diag(got) == 0.0).all()
+    numpy.testing.assert_allclose(got ** 2, jsdiv, rtol=1e-9, atol=1e-13)
+    numpy.testing.assert_allclose(c.adjacency_matrix(genes), co.adjacency_matrix(st, genes), rtol=1e-11, atol=0)
+    numpy.testing.assert_allclose(c.adjacency_matrix(genes[:5], ind=2), co.adjacency_matrix(st, genes[:5], ind=2), rtol=1e-11, atol=0)
+    sel = [g for g in genes if numpy.std(c.dicgenes[g]) > 0]         # a constant gene has no correlation distance
+    numpy.testing.assert_allclose(c.cor_matrix(sel), co.cor_matrix(st, sel), rtol=1e-9, atol=1e-12)
