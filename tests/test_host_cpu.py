@@ -159,3 +159,11 @@ def test_cover_bounds_device_form_is_numpy_percentile():
                         assert (a.numpy().view(numpy.int64) == numpy.ascontiguousarray(b).view(numpy.int64)).all()
                     lo0, hi0 = mo.intervals(mo.fenceposts(lens[:, 0], r, eq), gain)
                     assert (d[0].numpy() == lo0).all() and (d[1].numpy() == hi0).all()
+
+
+def test_package_exports_the_reference_names_on_the_path():
+    import sctda_b200 as scTDA
+    for name in ('TopologicalRepresentation', 'UnrootedGraph', 'RootedGraph', 'benjamini_hochberg'):
+        assert callable(getattr(scTDA, name))
+    with pytest.raises(AttributeError):
+        scTDA.Preprocess
