@@ -327,3 +327,25 @@ def test_gene_gene_matrices(golden_dir, tmp_path):
     numpy.testing.assert_allclose(c.adjacency_matrix(genes[:5], ind=2), co.adjacency_matrix(st, genes[:5], ind=2), rtol=1e-11, atol=0)
     sel = [g for g in genes if numpy.std(c.dicgenes[g]) > 0]         # a constant gene has no correlation distance
     numpy.testing.assert_allclose(c.cor_matrix(sel), co.cor_matrix(st, sel), rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.parametrize('n_cells', [30000, 60000])
+def test_large_components_use_the_other_staging_paths(n_cells):
+    """S = 30,000: the permutation row is staged in shared memory without double buffering;
+    S = 60,000: it does not fit and is gathered from global memory.  Both must give exactly the
+    counts and scores of the per-gene path (which the oracle tests pin) on a replicated block."""
+    ctx = _gpu()
+    from sctda_b200 import graph, synth
+    n_nodes, n_genes, n = 300, 40, 6
+    members, adj, Y = synth.connectivity_case(n_cells, n_nodes, n_genes, seed=13)
+    Yd = torch.from_numpy(Y).cuda()
+    dg = graph.DeviceGraph(members, adj, numpy.arange(n_cells), n_cells, 0)
+    rng = numpy.random.RandomState(2)
+    perms = torch.from_numpy(numpy.stack([rng.permutation(n_cells) for _ in range(n)]).astype(numpy.int32)).cuda()
+    st = graph.node_stats(ctx, dg, Yd, log2=True)
+    exa, tia, sca = graph.conn_perm_test(ctx, dg, Yd, perms, st['conn'], want_scores=True)
+    rep = perms.unsqueeze(0).repeat(n_genes, 1, 1).contiguous()
+    exb, tib, scb = graph.conn_perm_test(ctx, dg, Yd, rep, st['conn'], per_gene=True, want_scores=True)
+    assert torch.equal(exa, exb) and torch.equal(tia, tib)
+    assert torch.equal(torch.nan_to_num(sca), torch.nan_to_num(scb))
+    assert torch.isfinite(sca).any()
