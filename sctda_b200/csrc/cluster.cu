@@ -120,6 +120,7 @@ struct ClusterArgs {
     double* pgpp;
     int32_t* ppar;
     int8_t* lev_g;            // [Mtot][kMaxK-1]
+    int32_t* fine_rep;        // [nprob][kMaxK] smallest vertex of every cluster of the finest level
     int32_t* mst_parent;      // [Mtot] parent of local vertex u in the tree (-1 for the root)
     double* mst_w;            // [Mtot] weight of that edge
     int32_t* mst_order;       // [Mtot] insertion step of vertex u (-1 for the root)
@@ -396,30 +397,29 @@ __device__ __forceinline__ double masked_seq_sum(const double* __restrict__ v, i
 
 constexpr int kSelThreads = 1024;
 
-__global__ void __launch_bounds__(kSelThreads) select_kernel(ClusterArgs a) {
+// Kernel A of the selection: the (K_max - 1) heaviest tree edges and the labels of every level
+// (or, for the histogram-gap rule, the final labels).  One CTA per patch.
+__global__ void __launch_bounds__(kSelThreads) labels_kernel(ClusterArgs a) {
     extern __shared__ __align__(16) unsigned char s_dyn[];      // labels of every level: int8 [nlev][m]
     __shared__ double s_rk[32];
     __shared__ int s_ri[32], s_ro[32];
     __shared__ int s_heavy[kMaxK];               // vertices whose edge is the h-th heaviest
-    __shared__ int s_cof[kMaxK];                 // fine cluster -> coarse cluster of the level under evaluation
     __shared__ int s_fine_rep[kMaxK];
-    __shared__ double s_n[kMaxK];
-    __shared__ double s_cc[kMaxK][kMaxK];
-    __shared__ double s_S[kMaxK];
-    __shared__ double s_db[kMaxK];
+    __shared__ double s_cc[kMaxK][kMaxK];        // scratch of the histogram-gap reduction
     const int prob = a.prob0 + blockIdx.x;
     const int b = a.prob_bin[prob];
     const int off = a.bin_off[b], m = a.bin_off[b + 1] - off;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (m < 2) return;                           // handled by trivial_bins_kernel
-    const double* Gm = a.gram + a.gram_off[prob];
     const int kmax = m <= 5 ? 2 : min(m / 2, a.max_K);
     const int nlev = kmax - 1;                   // level L (0-based) = L+1 edges removed = L+2 clusters
     const double* w = a.mst_w + off;
     const int32_t* ord = a.mst_order + off;
     const int32_t* par = a.mst_parent + off;
     const int32_t* seq = a.mst_seq + off;
-    int8_t* lev = m > a.lev_cap ? a.lev_g + (size_t)off * (kMaxK - 1) : (int8_t*)s_dyn;
+    const bool lev_in_smem = (int64_t)m * (a.max_K - 1) <= a.lev_cap;
+    int8_t* lev_out = a.lev_g + (size_t)off * (kMaxK - 1);     // [nlev][m] in global memory for kernels B and C
+    int8_t* lev = lev_in_smem ? (int8_t*)s_dyn : lev_out;
     if (a.stat == 1) {
         // Histogram-gap cut (the rule BASELINE.json's north_star names; oracle cluster_bin(stat='histgap')):
         // edge lengths h = sqrt(d2) of the m-1 tree edges, 10 equal bins between min and max, every edge
@@ -518,14 +518,23 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(ClusterArgs a) {
         int cmin[kMaxK];
         cmin[0] = 0;
         lab[0] = 0;
-        for (int t = 1; t < m; ++t) {
-            const int v = seq[t];
-            bool cut = false;
-            for (int g = 0; g <= L; ++g) cut |= (s_heavy[g] == v);
-            int c;
-            if (cut) { c = ncomp; cmin[ncomp++] = v; }
-            else { c = lab[par[v]]; if (v < cmin[c]) cmin[c] = v; }
-            lab[v] = (int8_t)c;
+        for (int t0 = 1; t0 < m; t0 += 8) {               // seq / par do not depend on the walk: fetched 8 ahead
+            int vv[8], pp[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) vv[u] = t0 + u < m ? seq[t0 + u] : 0;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) pp[u] = t0 + u < m ? par[vv[u]] : 0;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                if (t0 + u >= m) break;
+                const int v = vv[u];
+                bool cut = false;
+                for (int g = 0; g <= L; ++g) cut |= (s_heavy[g] == v);
+                int c;
+                if (cut) { c = ncomp; cmin[ncomp++] = v; }
+                else { c = lab[pp[u]]; if (v < cmin[c]) cmin[c] = v; }
+                lab[v] = (int8_t)c;
+            }
         }
         int rank[kMaxK];
         for (int c = 0; c < ncomp; ++c) {
@@ -538,13 +547,35 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(ClusterArgs a) {
             for (int c = 0; c < ncomp; ++c) s_fine_rep[rank[c]] = cmin[c];
     }
     __syncthreads();
-    const int F = kmax;                                        // clusters of the finest level
-    const int8_t* fine = lev + (size_t)(nlev - 1) * m;
-    double* T = a.T + (int64_t)off * kMaxK;                    // [m][kMaxK]
-    double* TK = a.TK + (int64_t)off * kMaxK;                  // [m][kMaxK], per level
-    double* dist = a.dist + off;
-    // (e) T[p][f] = sum over q ascending of G[q][p] for q in fine cluster f
-    for (int p = tid; p < m; p += kSelThreads) {
+    if (lev_in_smem)
+        for (int i = tid; i < nlev * m; i += kSelThreads) lev_out[i] = lev[i];
+    if (tid < kmax) a.fine_rep[(int64_t)prob * kMaxK + tid] = s_fine_rep[tid];
+}
+
+// Kernel B: T[p][f] = sum over q ascending of G[q][p] for q in fine cluster f.  The columns of a patch
+// are independent: one CTA per 256 columns, so that a large patch streams its Gram tile through
+// many SMs instead of one (a single CTA sustains < 100 GB/s).
+constexpr int kColChunk = 256;
+
+__global__ void __launch_bounds__(kColChunk) tcol_kernel(ClusterArgs a, int nprob, const int64_t* __restrict__ chunk_prefix) {
+    const int64_t t = blockIdx.x;
+    int lo = 0, hi = nprob;                                   // last problem with chunk_prefix[p] <= t
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (chunk_prefix[mid] <= t) lo = mid; else hi = mid;
+    }
+    const int prob = lo;
+    const int b = a.prob_bin[prob];
+    const int off = a.bin_off[b], m = a.bin_off[b + 1] - off;
+    if (m < 2 || a.stat == 1) return;
+    const int p = (int)(t - chunk_prefix[prob]) * kColChunk + threadIdx.x;
+    const double* Gm = a.gram + a.gram_off[prob];
+    const int kmax = m <= 5 ? 2 : min(m / 2, a.max_K);
+    const int nlev = kmax - 1;
+    const int8_t* fine = a.lev_g + (size_t)off * (kMaxK - 1) + (size_t)(nlev - 1) * m;
+    double* T = a.T + (int64_t)off * kMaxK;
+    if (p >= m) return;
+    {
         double acc[kMaxK];
 #pragma unroll
         for (int f = 0; f < kMaxK; ++f) acc[f] = 0.0;
@@ -571,7 +602,31 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(ClusterArgs a) {
 #pragma unroll
         for (int f = 0; f < kMaxK; ++f) T[(int64_t)p * kMaxK + f] = acc[f];
     }
+}
+
+// Kernel C: Davies-Bouldin index of every level from T, choice of K, final labels.  One CTA per patch.
+__global__ void __launch_bounds__(kSelThreads) db_kernel(ClusterArgs a) {
+    __shared__ int s_cof[kMaxK];                 // fine cluster -> coarse cluster of the level under evaluation
+    __shared__ int s_fine_rep[kMaxK];
+    __shared__ double s_n[kMaxK];
+    __shared__ double s_cc[kMaxK][kMaxK];
+    __shared__ double s_S[kMaxK];
+    __shared__ double s_db[kMaxK];
+    const int prob = a.prob0 + blockIdx.x;
+    const int b = a.prob_bin[prob];
+    const int off = a.bin_off[b], m = a.bin_off[b + 1] - off;
+    const int tid = threadIdx.x;
+    if (m < 2 || a.stat == 1) return;
+    const double* Gm = a.gram + a.gram_off[prob];
+    const int kmax = m <= 5 ? 2 : min(m / 2, a.max_K);
+    const int nlev = kmax - 1;
+    const int8_t* lev = a.lev_g + (size_t)off * (kMaxK - 1);
+    if (tid < kmax) s_fine_rep[tid] = a.fine_rep[(int64_t)prob * kMaxK + tid];
     __syncthreads();
+    const int F = kmax;
+    double* T = a.T + (int64_t)off * kMaxK;                    // [m][kMaxK]
+    double* TK = a.TK + (int64_t)off * kMaxK;                  // [m][kMaxK], per level
+    double* dist = a.dist + off;
     // (f) Davies-Bouldin index of every level
     for (int L = 0; L < nlev; ++L) {
         const int K = L + 2;
@@ -868,12 +923,12 @@ extern "C" int32_t sctda_bin_cluster(sctda_ctx* ctx, int32_t G, const double* d_
     a.lev_g = (int8_t*)(a.ppar + M);
     a.labels = d_labels; a.bin_K = d_bin_K; a.bin_db = db;
     a.prim_cap = 0;                               // the generic kernel keeps its state in global memory
-    a.lev_cap = (80 * 1024 - 16) / (kMaxK - 1);
+    a.lev_cap = 160 * 1024 - 16;                  // bytes of shared memory for the level labels, (max_K - 1) * m per patch
     if (!(ctx->attr_done & 1u)) {
         SCTDA_CUDA(ctx, cudaFuncSetAttribute(prim_cluster_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024 - 1024));
         SCTDA_CUDA(ctx, cudaFuncSetAttribute(prim_cluster_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 136 * 1024));
         SCTDA_CUDA(ctx, cudaFuncSetAttribute(prim_reg_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        SCTDA_CUDA(ctx, cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
+        SCTDA_CUDA(ctx, cudaFuncSetAttribute(labels_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
         ctx->attr_done |= 1u;
     }
     // size classes of the MST kernels (a test hook lowers them so that small inputs reach every kernel)
@@ -888,15 +943,16 @@ extern "C" int32_t sctda_bin_cluster(sctda_ctx* ctx, int32_t G, const double* d_
         SCTDA_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
         for (int i = 0; i < 4; ++i) SCTDA_CUDA(ctx, cudaEventCreateWithFlags(&ctx->pipe_ev[i], cudaEventDisableTiming));
     }
-    cudaStream_t aux_st = ctx->aux_stream;
+
     // batches (host only)
-    struct Batch { size_t pos, end, elems; int max_lev; std::vector<int64_t> tiles, goff; };
+    struct Batch { size_t pos, end, elems; int max_lev; std::vector<int64_t> tiles, goff, chunks; };
     std::vector<Batch> batches;
     for (size_t pos = 0; pos < order.size();) {
         Batch bt;
         bt.pos = pos; bt.elems = 0; bt.max_lev = 0;
         bt.tiles.assign(1, 0);
         bt.goff.assign(1, 0);
+        bt.chunks.assign(1, 0);
         size_t end = pos;
         while (end < order.size()) {
             const int64_t m = h_off[order[end] + 1] - h_off[order[end]];
@@ -905,18 +961,25 @@ extern "C" int32_t sctda_bin_cluster(sctda_ctx* ctx, int32_t G, const double* d_
             const int64_t q = (m + 127) / 128;
             bt.tiles.push_back(bt.tiles.back() + q * (q + 1) / 2);            // upper-triangular 128x128 tiles
             bt.goff.push_back((int64_t)bt.elems);
-            if (m <= a.lev_cap && m > bt.max_lev) bt.max_lev = (int)m;
+            bt.chunks.push_back(bt.chunks.back() + (m + kColChunk - 1) / kColChunk);     // column chunks of the T kernel
+            if (m * (max_K - 1) <= a.lev_cap && m > bt.max_lev) bt.max_lev = (int)m;
             ++end;
         }
         bt.end = end;
         batches.push_back(std::move(bt));
         pos = end;
     }
+    // Two-stream pipeline (contraction of batch i+1 over the MST / selection of batch i): measured on
+    // B200 it gains 1 % on a 4-batch build and makes single-batch builds jitter by up to +30 % (the
+    // cross-stream hand-over), so it is opt-in (SCTDA_PIPELINE=1, at least two batches) and the
+    // default runs every kernel on the caller's stream.
+    const bool pipe = batches.size() >= 2 && getenv("SCTDA_PIPELINE") && atoi(getenv("SCTDA_PIPELINE")) != 0;
+    cudaStream_t aux_st = pipe ? ctx->aux_stream : st;
     // allocate both buffers up front (no reallocation while the pipeline runs)
     size_t need0 = 0, need1 = 0, meta0 = 0, meta1 = 0;
     for (size_t i = 0; i < batches.size(); ++i) {
         const size_t nbb = batches[i].end - batches[i].pos;
-        const size_t mb = (nbb + 1) * 16 + nbb * 4 + 64;
+        const size_t mb = (nbb + 1) * 24 + nbb * 4 + nbb * kMaxK * 4 + 64;
         if (i % 2 == 0) { need0 = std::max(need0, batches[i].elems * 8); meta0 = std::max(meta0, mb); }
         else { need1 = std::max(need1, batches[i].elems * 8); meta1 = std::max(meta1, mb); }
     }
@@ -928,18 +991,23 @@ extern "C" int32_t sctda_bin_cluster(sctda_ctx* ctx, int32_t G, const double* d_
         const Batch& bt = batches[i];
         const int k = (int)(i & 1);
         const int nb = (int)(bt.end - bt.pos);
-        if (i >= 2) SCTDA_CUDA(ctx, cudaStreamWaitEvent(st, ctx->pipe_ev[2 + k], 0));   // buffer k is free again
+        if (pipe && i >= 2) SCTDA_CUDA(ctx, cudaStreamWaitEvent(st, ctx->pipe_ev[2 + k], 0));   // buffer k is free again
         int64_t* d_tiles = (int64_t*)meta_buf[k];
         int64_t* d_goff = d_tiles + (nb + 1);
-        int32_t* d_prob = (int32_t*)(d_goff + (nb + 1));
+        int64_t* d_chunks = d_goff + (nb + 1);
+        int32_t* d_prob = (int32_t*)(d_chunks + (nb + 1));
+        a.fine_rep = d_prob + nb;
         SCTDA_CUDA(ctx, cudaMemcpyAsync(d_tiles, bt.tiles.data(), (size_t)(nb + 1) * 8, cudaMemcpyHostToDevice, st));
         SCTDA_CUDA(ctx, cudaMemcpyAsync(d_goff, bt.goff.data(), (size_t)(nb + 1) * 8, cudaMemcpyHostToDevice, st));
+        SCTDA_CUDA(ctx, cudaMemcpyAsync(d_chunks, bt.chunks.data(), (size_t)(nb + 1) * 8, cudaMemcpyHostToDevice, st));
         SCTDA_CUDA(ctx, cudaMemcpyAsync(d_prob, order.data() + bt.pos, (size_t)nb * 4, cudaMemcpyHostToDevice, st));
         a.prob_bin = d_prob; a.gram_off = d_goff; a.gram = gram_buf[k];
         int rc = sctda_internal_gram_bins(ctx, G, d_Xn, ldxn, nb, d_prob, d_bin_off, d_members, d_tiles, d_goff, gram_buf[k], st);
         if (rc) return rc;
-        SCTDA_CUDA(ctx, cudaEventRecord(ctx->pipe_ev[k], st));
-        SCTDA_CUDA(ctx, cudaStreamWaitEvent(aux_st, ctx->pipe_ev[k], 0));
+        if (pipe) {
+            SCTDA_CUDA(ctx, cudaEventRecord(ctx->pipe_ev[k], st));
+            SCTDA_CUDA(ctx, cudaStreamWaitEvent(aux_st, ctx->pipe_ev[k], 0));
+        }
         // MST: patches are sorted by size; [0,n_huge) above 28,000 cells (generic kernel, state in
         // global memory), [n_huge,n_big) above 16,384 and [n_big,n_mid) above 4,096 (one cluster of 8
         // CTAs per patch, 8 or 4 register keys per thread), the rest one CTA with 8 register keys
@@ -974,13 +1042,21 @@ extern "C" int32_t sctda_bin_cluster(sctda_ctx* ctx, int32_t G, const double* d_
             SCTDA_LAUNCH_CHECK(ctx, "prim_reg_kernel<8>");
         }
         a.prob0 = 0;
-        select_kernel<<<nb, kSelThreads, (size_t)bt.max_lev * (kMaxK - 1) + 16, aux_st>>>(a);
-        SCTDA_LAUNCH_CHECK(ctx, "select_kernel");
-        SCTDA_CUDA(ctx, cudaEventRecord(ctx->pipe_ev[2 + k], aux_st));
+        labels_kernel<<<nb, kSelThreads, (size_t)bt.max_lev * (max_K - 1) + 16, aux_st>>>(a);
+        SCTDA_LAUNCH_CHECK(ctx, "labels_kernel");
+        if (stat == 0) {
+            tcol_kernel<<<(unsigned)bt.chunks.back(), kColChunk, 0, aux_st>>>(a, nb, d_chunks);
+            SCTDA_LAUNCH_CHECK(ctx, "tcol_kernel");
+            db_kernel<<<nb, kSelThreads, 0, aux_st>>>(a);
+            SCTDA_LAUNCH_CHECK(ctx, "db_kernel");
+        }
+        if (pipe) SCTDA_CUDA(ctx, cudaEventRecord(ctx->pipe_ev[2 + k], aux_st));
     }
     // the caller's stream continues only after every batch is done
-    SCTDA_CUDA(ctx, cudaStreamWaitEvent(st, ctx->pipe_ev[2], 0));
-    if (batches.size() > 1) SCTDA_CUDA(ctx, cudaStreamWaitEvent(st, ctx->pipe_ev[3], 0));
+    if (pipe) {
+        SCTDA_CUDA(ctx, cudaStreamWaitEvent(st, ctx->pipe_ev[2], 0));
+        SCTDA_CUDA(ctx, cudaStreamWaitEvent(st, ctx->pipe_ev[3], 0));
+    }
     return SCTDA_OK;
 }
 
