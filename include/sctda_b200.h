@@ -60,6 +60,18 @@ int64_t sctda_workspace_bytes(const sctda_ctx* ctx);
  * (bench.py reports the per-step difference as "gpu_launches"). */
 int64_t sctda_launch_count(const sctda_ctx* ctx);
 
+/* Precision of the cells x cells contraction (BASELINE.json north_star (1)).
+ *   0  FP64 on the DMMA tensor pipe, one fused-multiply-add chain per element: the DEFAULT, the
+ *      Mapper graph is identical to the oracle's bit for bit;
+ *   1  opt-in 3xTF32 on the tcgen05 tensor cores (fp32 accumulation in TMEM): Gram entries of
+ *      unit-normalised rows / squared distances within 1e-5 of the FP64 result relative to
+ *      |x||y| (measured: tests/test_mapper_gpu.py); the graph is NOT guaranteed identical.
+ * Applies to sctda_bin_cluster and sctda_pairdist_rows_f64 of this context (sctda_gram_gather_f64
+ * always computes in FP64).  Replaces nothing in the reference: sakmapper / sklearn compute
+ * these distances in float64 (/root/reference/scTDA/main.py:746-751, 768-771). */
+int32_t sctda_set_precision(sctda_ctx* ctx, int32_t mode);
+int32_t sctda_get_precision(const sctda_ctx* ctx);
+
 /* Measurement aid (bench.py "roofline"): when enabled, every hot-path call brackets its
  * DOMINANT kernel (conn_perm_kernel for sctda_conn_perm_test) with CUDA events on the
  * caller's stream.  sctda_last_kernel_ms waits for that kernel to finish (host sync on

@@ -40,6 +40,8 @@ SIGNATURES = {
     'sctda_last_error': (ctypes.c_char_p, [c_ptr]),
     'sctda_workspace_bytes': (c_i64, [c_ptr]),
     'sctda_launch_count': (c_i64, [c_ptr]),
+    'sctda_set_precision': (c_i32, [c_ptr, c_i32]),
+    'sctda_get_precision': (c_i32, [c_ptr]),
     'sctda_set_kernel_timing': (c_i32, [c_ptr, c_i32]),
     'sctda_last_kernel_ms': (c_i32, [c_ptr, ctypes.POINTER(ctypes.c_float)]),
     'sctda_row_normalize_f64': (c_i32, [c_ptr, c_i32, c_i32, c_ptr, c_i64, c_i32, c_ptr, c_i64, c_ptr, c_ptr]),
@@ -118,6 +120,32 @@ class Context(object):
     def set_kernel_timing(self, enabled=True):
         self.check(self.lib.sctda_set_kernel_timing(self.handle, 1 if enabled else 0))
         self.timing_enabled = bool(enabled)
+
+    PRECISIONS = {'fp64': 0, '3xtf32': 1}
+
+    def set_precision(self, mode):
+        """'fp64' (default: graphs identical to the oracle) or '3xtf32' (opt-in tcgen05 contraction)."""
+        if mode not in self.PRECISIONS:
+            raise ValueError("precision must be 'fp64' or '3xtf32', got %r" % (mode,))
+        self.check(self.lib.sctda_set_precision(self.handle, self.PRECISIONS[mode]))
+
+    def precision(self, mode):
+        """Context manager: `with ctx.precision('3xtf32'): ...` (restores the previous mode)."""
+        import contextlib
+
+        @contextlib.contextmanager
+        def scope():
+            old = self.get_precision()
+            self.set_precision(mode)
+            try:
+                yield self
+            finally:
+                self.set_precision(old)
+        return scope()
+
+    def get_precision(self):
+        v = int(self.lib.sctda_get_precision(self.handle))
+        return [k for k, x in self.PRECISIONS.items() if x == v][0]
 
     def last_kernel_ms(self):
         ms = ctypes.c_float()

@@ -30,9 +30,17 @@
 
 int sctda_internal_gram_bins(sctda_ctx* ctx, int G, const double* d_Xn, int64_t ldxn, int nprob,
                              const int32_t* d_prob_bin, const int32_t* d_bin_off, const int32_t* d_members,
-                             const int64_t* d_tile_prefix, const int64_t* d_gram_off, double* d_gram, cudaStream_t st);
+                             const int64_t* d_tile_prefix, const int64_t* d_gram_off, double* d_gram, cudaStream_t st,
+                             int64_t nrows, bool reuse_split);
 
 namespace {
+
+__global__ void max_member_kernel(int64_t M, const int32_t* __restrict__ members, int32_t* __restrict__ out) {
+    int v = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < M; i += (int64_t)gridDim.x * blockDim.x) v = max(v, members[i]);
+    for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, v);
+}
 
 constexpr int kMaxK = 8;            // largest max_K served
 constexpr int kMaxRes = 128;        // largest resolution served (two 64-bit mask words per axis)
@@ -899,6 +907,21 @@ extern "C" int32_t sctda_bin_cluster(sctda_ctx* ctx, int32_t G, const double* d_
     // that the contraction of batch i+1 (caller's stream) overlaps the MST / selection kernels of
     // batch i (the context's auxiliary stream): the few largest patches bound the MST time of a
     // batch and would otherwise leave most SMs idle.
+    // opt-in 3xTF32 contraction (gemm_tf32.cu): it splits rows 0..max(member) of Xn into (hi, lo)
+    // operands once per call; reserve that workspace before the Gram buffers are sized
+    int64_t x_rows = 0;
+    if (ctx->precision == 1) {
+        int32_t* d_max = (int32_t*)sctda_ws(ctx, WS_MISC2, 256);
+        if (!d_max) return SCTDA_ERR_NOMEM;
+        SCTDA_CUDA(ctx, cudaMemsetAsync(d_max, 0, 4, st));
+        max_member_kernel<<<(unsigned)std::min<size_t>((M + 255) / 256, 1024), 256, 0, st>>>((int64_t)M, d_members, d_max);
+        SCTDA_LAUNCH_CHECK(ctx, "max_member_kernel");
+        int32_t h_max = 0;
+        SCTDA_CUDA(ctx, cudaMemcpyAsync(&h_max, d_max, 4, cudaMemcpyDeviceToHost, st));
+        SCTDA_CUDA(ctx, cudaStreamSynchronize(st));
+        x_rows = (int64_t)h_max + 1;
+        if (!sctda_ws(ctx, WS_SPLIT, (size_t)x_rows * ((G + 31) / 32) * 64 * sizeof(float))) return SCTDA_ERR_NOMEM;
+    }
     size_t free_b = 0, total_b = 0;
     SCTDA_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
     free_b += ctx->slot_bytes[WS_CLUSTER2] + ctx->slot_bytes[WS_CLUSTER4];
@@ -1002,7 +1025,8 @@ extern "C" int32_t sctda_bin_cluster(sctda_ctx* ctx, int32_t G, const double* d_
         SCTDA_CUDA(ctx, cudaMemcpyAsync(d_chunks, bt.chunks.data(), (size_t)(nb + 1) * 8, cudaMemcpyHostToDevice, st));
         SCTDA_CUDA(ctx, cudaMemcpyAsync(d_prob, order.data() + bt.pos, (size_t)nb * 4, cudaMemcpyHostToDevice, st));
         a.prob_bin = d_prob; a.gram_off = d_goff; a.gram = gram_buf[k];
-        int rc = sctda_internal_gram_bins(ctx, G, d_Xn, ldxn, nb, d_prob, d_bin_off, d_members, d_tiles, d_goff, gram_buf[k], st);
+        int rc = sctda_internal_gram_bins(ctx, G, d_Xn, ldxn, nb, d_prob, d_bin_off, d_members, d_tiles, d_goff, gram_buf[k], st,
+                                          x_rows, i > 0);
         if (rc) return rc;
         if (pipe) {
             SCTDA_CUDA(ctx, cudaEventRecord(ctx->pipe_ev[k], st));

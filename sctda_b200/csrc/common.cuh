@@ -23,6 +23,7 @@ struct sctda_ctx {
     unsigned attr_done;                  // per-context (= per-device) one-time kernel attribute setup, one bit per file
     cudaStream_t aux_stream;             // second stream for the patch pipeline (cluster.cu)
     cudaEvent_t pipe_ev[4];
+    int precision;                       // sctda_set_precision: 0 = FP64 (bit-exact, default), 1 = 3xTF32 contraction
 };
 
 // Workspace slots (one live use per call; calls on one context are serialised by contract).
@@ -38,6 +39,8 @@ enum {
     WS_NODES = 9,
     WS_CLUSTER4 = 10,   // second Gram buffer of the patch pipeline
     WS_CLUSTER5 = 11,   // second batch-metadata buffer
+    WS_MISC2 = 13,
+    WS_SPLIT = 12,      // (hi, lo) TF32 operands of the opt-in 3xTF32 contraction
 };
 
 static inline int sctda_fail(sctda_ctx* ctx, int code, const char* fmt, const char* a = "", long long b = 0) {

@@ -58,6 +58,15 @@ extern "C" int64_t sctda_workspace_bytes(const sctda_ctx* ctx) {
 
 extern "C" int64_t sctda_launch_count(const sctda_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+extern "C" int32_t sctda_set_precision(sctda_ctx* ctx, int32_t mode) {
+    if (!ctx) return SCTDA_ERR_INVALID;
+    if (mode != 0 && mode != 1) return sctda_fail(ctx, SCTDA_ERR_UNSUPPORTED, "set_precision: 0 (FP64) or 1 (3xTF32)%s");
+    ctx->precision = mode;
+    return SCTDA_OK;
+}
+
+extern "C" int32_t sctda_get_precision(const sctda_ctx* ctx) { return ctx ? ctx->precision : SCTDA_ERR_INVALID; }
+
 extern "C" int32_t sctda_set_kernel_timing(sctda_ctx* ctx, int32_t enabled) {
     if (!ctx) return SCTDA_ERR_INVALID;
     if (enabled && !ctx->tev[0]) {

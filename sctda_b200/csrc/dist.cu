@@ -22,6 +22,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "gemm.cuh"
 
 namespace {
 
@@ -29,8 +30,6 @@ constexpr int BM = 128, BN = 128, BK = 16, LDS = 20, STAGES = 3;
 constexpr int GEMM_THREADS = 256;
 constexpr int STAGE_DOUBLES = (BM + BN) * LDS;
 constexpr size_t GEMM_SMEM = (size_t)STAGES * STAGE_DOUBLES * sizeof(double);
-
-enum { EPI_GRAM = 0, EPI_EUCLID = 1, EPI_CORR = 2 };
 
 __device__ __forceinline__ void cp_async_16_zfill(void* smem_dst, const void* gmem_src, int src_bytes) {
     unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -70,33 +69,6 @@ __device__ __forceinline__ void dmma_884(double& d0, double& d1, double a, doubl
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                  : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
-
-// One batched problem: out[i][j] for i < na, j < nb.
-struct GemmProblem {
-    const int32_t* rows_a;   // row indices into X (NULL: identity + row0_a)
-    const int32_t* rows_b;
-    int row0_a, row0_b;
-    int na, nb;
-    double* out;
-    int64_t ldo;
-};
-
-struct GemmArgs {
-    const double* X;         // [*, ldx]
-    int64_t ldx;
-    int G;                   // features (K of the GEMM)
-    const double* sq;        // |row|^2 (EUCLID epilogue)
-    int epilogue;
-    // single problem (nprob == 0) or batched patches
-    GemmProblem single;
-    int nprob;
-    const int32_t* prob_bin;     // [nprob] patch index of problem p
-    const int32_t* bin_off;      // member offsets of all patches
-    const int32_t* members;      // [Mtot]
-    const int64_t* tile_prefix;  // [nprob+1] number of upper-triangular 128x128 tiles before problem p
-    const int64_t* gram_off;     // [nprob+1] element offset of problem p's m x m output
-    double* gram;
-};
 
 // BULK: every K stage is a full 16 columns (the caller guarantees zero padding up to a multiple
 // of 16) and is staged by warp 0 with one 128-byte TMA bulk copy per row, completing on the
@@ -317,7 +289,8 @@ __global__ void __launch_bounds__(256) row_normalize_kernel(const double* __rest
 }
 
 // bulk: the rows are zero-padded to a multiple of 16 columns (ldx >= roundup16(G)), every K stage is full
-int launch_gemm(sctda_ctx* ctx, const GemmArgs& a, int64_t tiles_hint, cudaStream_t st, bool bulk) {
+int launch_gemm(sctda_ctx* ctx, const GemmArgs& a, int64_t tiles_hint, cudaStream_t st, bool bulk, bool reuse_split = false) {
+    if (ctx->precision == 1 && a.nrows > 0) return sctda_launch_gemm_tf32(ctx, a, st, reuse_split);   // opt-in 3xTF32 (gemm_tf32.cu)
     if (!(ctx->attr_done & 2u)) {
         SCTDA_CUDA(ctx, cudaFuncSetAttribute(gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
         SCTDA_CUDA(ctx, cudaFuncSetAttribute(gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
@@ -344,13 +317,14 @@ int launch_gemm(sctda_ctx* ctx, const GemmArgs& a, int64_t tiles_hint, cudaStrea
 // Batched patch Gram matrices for the clustering stage (cluster.cu).
 int sctda_internal_gram_bins(sctda_ctx* ctx, int G, const double* d_Xn, int64_t ldxn, int nbins,
                              const int32_t* d_prob_bin, const int32_t* d_bin_off, const int32_t* d_members,
-                             const int64_t* d_tile_prefix, const int64_t* d_gram_off, double* d_gram, cudaStream_t st) {
+                             const int64_t* d_tile_prefix, const int64_t* d_gram_off, double* d_gram, cudaStream_t st,
+                             int64_t nrows, bool reuse_split) {
     GemmArgs a;
     memset(&a, 0, sizeof(a));
-    a.X = d_Xn; a.ldx = ldxn; a.G = G; a.epilogue = EPI_GRAM;
+    a.X = d_Xn; a.ldx = ldxn; a.G = G; a.epilogue = EPI_GRAM; a.nrows = nrows;
     a.nprob = nbins; a.prob_bin = d_prob_bin; a.bin_off = d_bin_off; a.members = d_members;
     a.tile_prefix = d_tile_prefix; a.gram_off = d_gram_off; a.gram = d_gram;
-    return launch_gemm(ctx, a, 0, st, ldxn >= ((int64_t)G + 15) / 16 * 16);
+    return launch_gemm(ctx, a, 0, st, ldxn >= ((int64_t)G + 15) / 16 * 16, reuse_split);
 }
 
 extern "C" int32_t sctda_row_normalize_f64(sctda_ctx* ctx, int32_t N, int32_t G, const double* d_X, int64_t ldx,
@@ -399,7 +373,7 @@ extern "C" int32_t sctda_pairdist_rows_f64(sctda_ctx* ctx, int32_t N, int32_t G,
     SCTDA_CUDA(ctx, cudaSetDevice(ctx->device));
     GemmArgs a;
     memset(&a, 0, sizeof(a));
-    a.X = d_Xn; a.ldx = ldxn; a.G = G; a.sq = d_sq;
+    a.X = d_Xn; a.ldx = ldxn; a.G = G; a.sq = d_sq; a.nrows = N;
     a.epilogue = metric == 0 ? EPI_EUCLID : EPI_CORR;
     a.single.row0_a = r0; a.single.na = r1 - r0; a.single.row0_b = 0; a.single.nb = N;
     a.single.out = d_D; a.single.ldo = ldd;

@@ -1,0 +1,39 @@
+// Problem description shared by the two contraction kernels: the FP64 DMMA kernel (dist.cu, the
+// default, bit-exact against the oracle) and the opt-in 3xTF32 tcgen05 kernel (gemm_tf32.cu).
+#pragma once
+#include "common.cuh"
+
+enum { EPI_GRAM = 0, EPI_EUCLID = 1, EPI_CORR = 2 };
+
+// One batched problem: out[i][j] for i < na, j < nb.
+struct GemmProblem {
+    const int32_t* rows_a;   // row indices into X (NULL: identity + row0_a)
+    const int32_t* rows_b;
+    int row0_a, row0_b;
+    int na, nb;
+    double* out;
+    int64_t ldo;
+};
+
+struct GemmArgs {
+    const double* X;         // [*, ldx]
+    int64_t nrows;           // rows of X (needed by the 3xTF32 operand split; 0 = unknown)
+    int64_t ldx;
+    int G;                   // features (K of the GEMM)
+    const double* sq;        // |row|^2 (EUCLID epilogue)
+    int epilogue;
+    // single problem (nprob == 0) or batched patches
+    GemmProblem single;
+    int nprob;
+    const int32_t* prob_bin;     // [nprob] patch index of problem p
+    const int32_t* bin_off;      // member offsets of all patches
+    const int32_t* members;      // [Mtot]
+    const int64_t* tile_prefix;  // [nprob+1] number of upper-triangular 128x128 tiles before problem p
+    const int64_t* gram_off;     // [nprob+1] element offset of problem p's m x m output
+    double* gram;
+};
+
+
+// gemm_tf32.cu: same problems, 3xTF32 on the tcgen05 tensor cores (sctda_set_precision(ctx, 1)).
+// reuse_split: the (hi, lo) operands of this X are already in the workspace (later batches of one call).
+int sctda_launch_gemm_tf32(sctda_ctx* ctx, const GemmArgs& a, cudaStream_t st, bool reuse_split);

@@ -1,0 +1,380 @@
+// Hot path (a), stage 1, OPT-IN precision: the cells x cells Gram / distance contraction as
+// 3xTF32 on the 5th-generation tensor cores (tcgen05.mma kind::tf32, accumulators in TMEM).
+//
+// BASELINE.json north_star (1): "... an opt-in FP32/3xTF32 mode at a stated <= 1e-5 relative
+// tolerance".  The default stays the FP64 DMMA kernel of dist.cu (bit-exact against the oracle);
+// sctda_set_precision(ctx, 1) routes the same problems (patch Gram tiles for the clustering of
+// /root/reference/scTDA/main.py:768-771, distance row blocks for the MDS lens of :746-751) here.
+//
+// Arithmetic.  Every normalised value x (float64) is split once into two TF32 numbers,
+//     hi = tf32(x),  lo = tf32(x - hi)            (22 significand bits between them)
+// and  x.y ~= hi.hi' + (hi.lo' + lo.hi')  -- three tensor-core products, the dropped lo.lo' term is
+// 2^-22 relative.  The large and the small products accumulate in SEPARATE fp32 TMEM accumulators
+// (so the cross terms are not absorbed by the rounding of the big sum) and are added in float64 in
+// the epilogue, which then applies the same Gram / euclidean / correlation epilogue as dist.cu.
+//
+// fp32 accumulation in the tensor core truncates: over K = 5,000 (625 accumulation steps) a single
+// accumulator drifts by 4e-5 (measured).  The K loop is therefore cut into SEGMENTS of 256 features
+// that alternate between the two TMEM accumulator stages; the epilogue warps drain each finished
+// segment into float64 register sums while the next segment's MMAs run (measured error: see the
+// header, sctda_set_precision).
+//
+// Kernel (sm_100a), persistent, one CTA per SM, 352 threads in three roles:
+//   warps 8-9  producers: gather operand rows (index lists: a tiled TMA box cannot express them)
+//              with 16-byte cp.async into the canonical K-major SWIZZLE_128B layout the UMMA
+//              shared-memory descriptors expect, 3-stage ring of 64 KB (K = 32 per stage:
+//              A_hi, A_lo, B_hi, B_lo blocks of 128 rows x 128 bytes);
+//   warp 10    one elected thread issues tcgen05.mma: per K = 8 step
+//                  D[:, 0:256)   += A_hi . [B_hi ; B_lo]^T     (M128 N256: hi.hi and hi.lo in one issue)
+//                  D[:, 128:256) += A_lo . B_hi^T             (M128 N128)
+//              and tcgen05.commit releases the stage / publishes the accumulator;
+//   warps 0-7  epilogue: warp w owns TMEM lanes 32*(w%4).. and columns 64*(w/4)..; per segment
+//              tcgen05.ld + float64 accumulation of both accumulators (64 sums per thread), at the
+//              end of the tile the epilogue transform and direct + mirrored (symmetric) float64 stores.
+// TMEM: 2 accumulator stages x 256 columns = all 512 columns, so draining segment s overlaps the
+// MMAs of segment s+1 (also across tiles).  Every mbarrier wait is bounded (trap after ~4 s) so a protocol bug
+// cannot hang the device.
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "gemm.cuh"
+
+namespace {
+
+constexpr int TM = 128, TN = 128, KC = 32;
+constexpr int T_STAGES = 3, LAG = 2;
+constexpr int BLK_BYTES = TM * KC * 4;                  // 16 KB, one swizzled 128-row block
+constexpr int STAGE_BYTES = 4 * BLK_BYTES;              // A_hi, A_lo, B_hi, B_lo
+constexpr int EPI_THREADS = 256, PROD_THREADS = 64, MMA_WARP = (EPI_THREADS + PROD_THREADS) / 32;
+constexpr int T_THREADS = EPI_THREADS + PROD_THREADS + 32;
+constexpr int SEG = 8;                                  // K chunks (256 features) per fp32 accumulation segment
+constexpr size_t T_SMEM = (size_t)T_STAGES * STAGE_BYTES + 1024;
+constexpr int ACC_COLS = 256;                           // fp32 columns per accumulator stage
+
+struct TArgs {
+    GemmArgs g;
+    const uint4* Xs;        // split operands: [row][kchunk][hi 32 floats | lo 32 floats]
+    int kchunks;            // ceil(G / 32)
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    const uint32_t addr = smem_u32(bar);
+    const long long t0 = clock64();
+    for (;;) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+        if (ok) return;
+        if (clock64() - t0 > 8000000000LL) __trap();      // ~4 s: a protocol bug must not hang the device
+    }
+}
+__device__ __forceinline__ void cp_async_16(uint32_t smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor: 8-row groups of 1,024 bytes (SBO),
+// descriptor version 1 (sm_100), start address in 16-byte units.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// kind::tf32, fp32 accumulate, A and B K-major, M = 128
+__device__ __forceinline__ constexpr uint32_t umma_idesc(int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+struct Tile {
+    GemmProblem pr;
+    int ti, tj;
+    bool mirror;
+};
+
+// tile t of the launch -> problem and tile coordinates (same enumeration as dist.cu: a single
+// rectangular problem, or the upper triangles of the patches' tile grids)
+__device__ __forceinline__ Tile decode_tile(const GemmArgs& a, int64_t t) {
+    Tile o;
+    if (a.nprob == 0) {
+        const int tn = (a.single.nb + TN - 1) / TN;
+        o.pr = a.single;
+        o.ti = (int)(t / tn);
+        o.tj = (int)(t % tn);
+        o.mirror = false;
+        return o;
+    }
+    int lo = 0, hi = a.nprob;
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (a.tile_prefix[mid] <= t) lo = mid; else hi = mid;
+    }
+    const int bin = a.prob_bin[lo];
+    const int m = a.bin_off[bin + 1] - a.bin_off[bin];
+    const int tn = (m + TN - 1) / TN;
+    int64_t lt = t - a.tile_prefix[lo];
+    int ti = 0;
+    while (lt >= tn - ti) { lt -= tn - ti; ++ti; }
+    o.ti = ti;
+    o.tj = ti + (int)lt;
+    o.mirror = o.ti != o.tj;
+    o.pr.rows_a = o.pr.rows_b = a.members + a.bin_off[bin];
+    o.pr.row0_a = o.pr.row0_b = 0;
+    o.pr.na = o.pr.nb = m;
+    o.pr.out = a.gram + a.gram_off[lo];
+    o.pr.ldo = m;
+    return o;
+}
+
+__device__ __forceinline__ int64_t total_tiles(const GemmArgs& a) {
+    if (a.nprob == 0) return (int64_t)((a.single.na + TM - 1) / TM) * ((a.single.nb + TN - 1) / TN);
+    return a.tile_prefix[a.nprob];
+}
+
+__global__ void __launch_bounds__(T_THREADS, 1) gemm_tf32x3_kernel(TArgs ta) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar_full[T_STAGES], bar_empty[T_STAGES], bar_tfull[2], bar_tempty[2];
+    __shared__ uint32_t tmem_base_s;
+    const GemmArgs& a = ta.g;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;     // SWIZZLE_128B blocks are 1,024-byte aligned
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < T_STAGES; ++s) { mbar_init(bar_full + s, PROD_THREADS); mbar_init(bar_empty + s, 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(bar_tfull + s, 1); mbar_init(bar_tempty + s, EPI_THREADS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == MMA_WARP) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+    const int64_t total = total_tiles(a);
+    const int kchunks = ta.kchunks;
+
+    if (warp >= EPI_THREADS / 32 && warp < MMA_WARP) {
+        // ---------------- producers ----------------
+        const int pt = threadIdx.x - EPI_THREADS;
+        const int piece = pt & 15, rsub = pt >> 4;                     // 16 x 16-byte pieces of a row's 256-byte K chunk
+        constexpr int RSTEP = PROD_THREADS / 16;                        // rows covered per pass of the producer threads
+        constexpr int NR = 2 * TM / RSTEP;                              // copies per thread and stage (A rows, then B rows)
+        const uint32_t dst_blk = (uint32_t)((piece >> 3) * BLK_BYTES);
+        uint32_t it = 0;
+        for (int64_t t = blockIdx.x; t < total; t += gridDim.x) {
+            const Tile tl = decode_tile(a, t);
+            const int m0 = tl.ti * TM, n0 = tl.tj * TN;
+            uint32_t roff[NR];                                          // source offsets in 16-byte units
+#pragma unroll
+            for (int i = 0; i < NR / 2; ++i) {
+                const int ra = min(m0 + rsub + RSTEP * i, tl.pr.na - 1), rb = min(n0 + rsub + RSTEP * i, tl.pr.nb - 1);
+                const uint32_t ga = tl.pr.rows_a ? (uint32_t)tl.pr.rows_a[ra] : (uint32_t)(tl.pr.row0_a + ra);
+                const uint32_t gb = tl.pr.rows_b ? (uint32_t)tl.pr.rows_b[rb] : (uint32_t)(tl.pr.row0_b + rb);
+                roff[i] = ga * (uint32_t)(kchunks * 16) + piece;
+                roff[NR / 2 + i] = gb * (uint32_t)(kchunks * 16) + piece;
+            }
+            for (int kb = 0; kb < kchunks; ++kb, ++it) {
+                const uint32_t s = it % T_STAGES;
+                mbar_wait(bar_empty + s, ((it / T_STAGES) & 1) ^ 1);
+                const uint32_t dst = smem0 + s * STAGE_BYTES + dst_blk;
+                const uint4* src = ta.Xs + kb * 16;
+#pragma unroll
+                for (int i = 0; i < NR; ++i) {
+                    const int rr = rsub + RSTEP * (i % (NR / 2));       // row within the 128-row block
+                    cp_async_16(dst + (i / (NR / 2)) * (2 * BLK_BYTES) + rr * 128 + (((piece & 7) ^ (rr & 7)) << 4), src + roff[i]);
+                }
+                cp_async_commit();
+                if (it >= LAG) {
+                    cp_async_wait<LAG>();
+                    fence_proxy_async();
+                    mbar_arrive(bar_full + (it - LAG) % T_STAGES);
+                }
+            }
+        }
+        // drain: the last LAG stages
+        if (it >= 2) { cp_async_wait<1>(); fence_proxy_async(); mbar_arrive(bar_full + (it - 2) % T_STAGES); }
+        if (it >= 1) { cp_async_wait<0>(); fence_proxy_async(); mbar_arrive(bar_full + (it - 1) % T_STAGES); }
+    } else if (warp == MMA_WARP) {
+        // ---------------- MMA issuer ----------------
+        if (lane == 0) {
+            uint32_t it = 0, segcount = 0;
+            const uint32_t idesc256 = umma_idesc(256), idesc128 = umma_idesc(128);
+            for (int64_t t = blockIdx.x; t < total; t += gridDim.x) {
+                for (int k0 = 0; k0 < kchunks; k0 += SEG, ++segcount) {
+                    const uint32_t as = segcount & 1;
+                    mbar_wait(bar_tempty + as, ((segcount >> 1) & 1) ^ 1);
+                    tc_fence_after();
+                    const uint32_t d = tmem_base + as * ACC_COLS;
+                    const int k1 = min(k0 + SEG, kchunks);
+                    for (int kb = k0; kb < k1; ++kb, ++it) {
+                        const uint32_t s = it % T_STAGES;
+                        mbar_wait(bar_full + s, (it / T_STAGES) & 1);
+                        tc_fence_after();
+                        const uint32_t base = smem0 + s * STAGE_BYTES;
+#pragma unroll
+                        for (int k = 0; k < KC / 8; ++k) {
+                            const uint64_t a_hi = umma_desc(base + k * 32);
+                            const uint64_t a_lo = umma_desc(base + BLK_BYTES + k * 32);
+                            const uint64_t b_hl = umma_desc(base + 2 * BLK_BYTES + k * 32);
+                            umma_tf32(d, a_hi, b_hl, idesc256, (kb > k0 || k > 0) ? 1u : 0u);
+                            umma_tf32(d + 128, a_lo, b_hl, idesc128, 1u);
+                        }
+                        umma_commit(bar_empty + s);                     // the stage is free when these MMAs have read it
+                    }
+                    umma_commit(bar_tfull + as);                        // this K segment's accumulators are complete
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ---------------- epilogue: float64 running sums over the K segments ----------------
+        uint32_t segcount = 0;
+        const int quarter = warp & 3, half = warp >> 2;                 // TMEM lanes 32*quarter.., columns 64*half..
+        for (int64_t t = blockIdx.x; t < total; t += gridDim.x) {
+            const Tile tl = decode_tile(a, t);
+            double acc[64];
+#pragma unroll
+            for (int j = 0; j < 64; ++j) acc[j] = 0.0;
+            for (int k0 = 0; k0 < kchunks; k0 += SEG, ++segcount) {
+                const uint32_t as = segcount & 1;
+                mbar_wait(bar_tfull + as, (segcount >> 1) & 1);
+                __syncwarp();                                           // tcgen05.ld is warp-collective
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * ACC_COLS + half * 64;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t big[16], small[16];
+                    tmem_ld16(taddr + c * 16, big);
+                    tmem_ld16(taddr + 128 + c * 16, small);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        acc[c * 16 + j] += (double)__uint_as_float(big[j]) + (double)__uint_as_float(small[j]);
+                }
+                tc_fence_before();
+                mbar_arrive(bar_tempty + as);
+            }
+            const int r = tl.ti * TM + quarter * 32 + lane;
+            if (r < tl.pr.na) {
+                const int64_t gr = tl.pr.rows_a ? (int64_t)tl.pr.rows_a[r] : (int64_t)(tl.pr.row0_a + r);
+                const double sqr = (a.epilogue == EPI_EUCLID) ? a.sq[gr] : 0.0;
+                const int c0 = tl.tj * TN + half * 64;
+                double* orow = tl.pr.out + (int64_t)r * tl.pr.ldo + c0;
+#pragma unroll
+                for (int j = 0; j < 64; ++j) {
+                    if (c0 + j >= tl.pr.nb) continue;
+                    double v = acc[j];
+                    if (a.epilogue != EPI_GRAM) {
+                        const int64_t gc = tl.pr.rows_b ? (int64_t)tl.pr.rows_b[c0 + j] : (int64_t)(tl.pr.row0_b + c0 + j);
+                        if (a.epilogue == EPI_EUCLID) v = sqrt(fmax(fma(-2.0, v, sqr + a.sq[gc]), 0.0));
+                        else v = 1.0 - v;
+                        if (gr == gc) v = 0.0;
+                    }
+                    orow[j] = v;
+                    if (tl.mirror) tl.pr.out[(int64_t)(c0 + j) * tl.pr.ldo + r] = v;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == MMA_WARP) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// x -> (tf32(x), tf32(x - tf32(x))), laid out [row][K chunk of 32][hi 32 | lo 32], zero padded in K
+__global__ void __launch_bounds__(256) split_tf32_kernel(const double* __restrict__ X, int64_t ldx, int64_t nrows, int G,
+                                                         int kchunks, float* __restrict__ Xs) {
+    const int64_t per_row = (int64_t)kchunks * 32;
+    const int64_t total = nrows * per_row;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = e / per_row;
+        const int k = (int)(e - row * per_row);
+        const double x = k < G ? X[row * ldx + k] : 0.0;
+        uint32_t hi, lo;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"((float)x));
+        const double rest = x - (double)__uint_as_float(hi);
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"((float)rest));
+        float* dst = Xs + row * per_row * 2 + (int64_t)(k >> 5) * 64 + (k & 31);
+        dst[0] = __uint_as_float(hi);
+        dst[32] = __uint_as_float(lo);
+    }
+}
+
+}  // namespace
+
+int sctda_launch_gemm_tf32(sctda_ctx* ctx, const GemmArgs& a, cudaStream_t st, bool reuse_split) {
+    if (a.nrows <= 0) return sctda_fail(ctx, SCTDA_ERR_UNSUPPORTED, "3xTF32 contraction: the row count of X is unknown%s");
+    const int kchunks = (a.G + KC - 1) / KC;
+    if ((double)a.nrows * kchunks * 16.0 >= 4294967296.0)
+        return sctda_fail(ctx, SCTDA_ERR_UNSUPPORTED, "3xTF32 contraction: operand too large for 32-bit row offsets%s");
+    if (!(ctx->attr_done & 64u)) {
+        SCTDA_CUDA(ctx, cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T_SMEM));
+        ctx->attr_done |= 64u;
+    }
+    float* Xs = (float*)sctda_ws(ctx, WS_SPLIT, (size_t)a.nrows * kchunks * 64 * sizeof(float));
+    if (!Xs) return SCTDA_ERR_NOMEM;
+    const int64_t elems = a.nrows * (int64_t)kchunks * 32;
+    int64_t sgrid = cdiv64(elems, 256);
+    if (sgrid > (int64_t)ctx->sm_count * 16) sgrid = (int64_t)ctx->sm_count * 16;
+    if (!reuse_split) {
+        split_tf32_kernel<<<(unsigned)sgrid, 256, 0, st>>>(a.X, a.ldx, a.nrows, a.G, kchunks, Xs);
+        SCTDA_LAUNCH_CHECK(ctx, "split_tf32_kernel");
+    }
+    TArgs ta;
+    ta.g = a;
+    ta.Xs = (const uint4*)Xs;
+    ta.kchunks = kchunks;
+    SCTDA_TIME_BEGIN(ctx, st);
+    gemm_tf32x3_kernel<<<(unsigned)ctx->sm_count, T_THREADS, T_SMEM, st>>>(ta);
+    SCTDA_TIME_END(ctx, st);
+    SCTDA_LAUNCH_CHECK(ctx, "gemm_tf32x3_kernel");
+    return SCTDA_OK;
+}

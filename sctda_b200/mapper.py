@@ -82,6 +82,8 @@ def pairwise_distances(ctx, Xd, metric, row_block=8192):
     n, g = Xn.shape
     D = torch.empty((n, n), dtype=torch.float64, device=dev)
     code = {'euclidean': 0, 'correlation': 1}[metric]
+    if ctx.get_precision() != 'fp64':
+        row_block = n                 # the 3xTF32 path splits the operands once per call
     for r0 in range(0, n, row_block):
         r1 = min(n, r0 + row_block)
         ctx.check(ctx.lib.sctda_pairdist_rows_f64(ctx.handle, n, g, _lib.ptr(Xn), int(Xn.stride(0)), _lib.ptr(sq), r0, r1,
@@ -453,11 +455,13 @@ def pca_lens_device(Xd):
 
 
 def mapper_graph(df, lens_data, resolution=10, gain=0.5, equalize=True, clust='agglomerative', stat='db', max_K=5,
-                 metric='euclidean', device=0, verbose=True):
+                 metric='euclidean', device=0, verbose=True, precision='fp64'):
     """sakmapper.mapper_graph as called at ref:768-771 -> (G, all_clusters, patches):
     G networkx.Graph with nodes 0..V-1 and weight-1.0 edges, all_clusters[k] the ascending row
     positions of node k, patches {(i, j): row positions of cover patch (i, j)}.
-    `metric` (extension): distances used by the per-patch clustering."""
+    `metric` (extension): distances used by the per-patch clustering.
+    `precision` (extension): 'fp64' (default, graph identical to the oracle) or '3xtf32' (opt-in
+    tcgen05 contraction, distances within 1e-5; see include/sctda_b200.h sctda_set_precision)."""
     import networkx
     if clust != 'agglomerative':
         raise NotImplementedError("clust=%r: the device path clusters by single linkage ('agglomerative')" % (clust,))
@@ -465,7 +469,8 @@ def mapper_graph(df, lens_data, resolution=10, gain=0.5, equalize=True, clust='a
     dev = torch.device('cuda', device)
     Xd = _padded_device_table(_values(df), dev)
     lens = numpy.asarray(_values(lens_data), dtype=numpy.float64)[:, :2]
-    res = build_graph_device(ctx, Xd, lens, resolution, gain, equalize=equalize, stat=stat, max_K=max_K, metric=metric)
+    with ctx.precision(precision):
+        res = build_graph_device(ctx, Xd, lens, resolution, gain, equalize=equalize, stat=stat, max_K=max_K, metric=metric)
     bin_off = res.bin_off.cpu().numpy()
     members = res.members.cpu().numpy()
     node_off = res.node_off.cpu().numpy()
@@ -506,11 +511,11 @@ class TopologicalRepresentation(object):
             self.lens_data_mds = apply_lens(self.df, lens=lens, device=device, **kwargs)
 
     def save(self, name, resolution, gain, equalize=True, cluster='agglomerative', statistics='db', max_K=5,
-             cluster_metric='euclidean'):
+             cluster_metric='euclidean', precision='fp64'):
         """ref:758-778: writes name.json and name.gexf, returns the patches."""
         G, all_clusters, patches = mapper_graph(self.df, lens_data=self.lens_data_mds, resolution=resolution, gain=gain,
                                                 equalize=equalize, clust=cluster, stat=statistics, max_K=max_K,
-                                                metric=cluster_metric, device=self.device)
+                                                metric=cluster_metric, device=self.device, precision=precision)
         formats.write_mapper_json(name + '.json', all_clusters)                  # ref:772-776
         formats.write_gexf(name + '.gexf', G.number_of_nodes(), sorted(G.edges()))   # ref:777
         return patches
