@@ -121,12 +121,13 @@ class Context(object):
         self.check(self.lib.sctda_set_kernel_timing(self.handle, 1 if enabled else 0))
         self.timing_enabled = bool(enabled)
 
-    PRECISIONS = {'fp64': 0, '3xtf32': 1}
+    PRECISIONS = {'fp64': 0, 'fp16x3': 1, '3xtf32': 1}      # '3xtf32': the north star's name for the same 22-bit split
 
     def set_precision(self, mode):
-        """'fp64' (default: graphs identical to the oracle) or '3xtf32' (opt-in tcgen05 contraction)."""
+        """'fp64' (default: graphs identical to the oracle) or 'fp16x3' (opt-in tcgen05 contraction of
+        (hi, lo) half-precision operand pairs, alias '3xtf32'; see sctda_set_precision in the header)."""
         if mode not in self.PRECISIONS:
-            raise ValueError("precision must be 'fp64' or '3xtf32', got %r" % (mode,))
+            raise ValueError("precision must be 'fp64' or 'fp16x3', got %r" % (mode,))
         self.check(self.lib.sctda_set_precision(self.handle, self.PRECISIONS[mode]))
 
     def precision(self, mode):
@@ -145,7 +146,7 @@ class Context(object):
 
     def get_precision(self):
         v = int(self.lib.sctda_get_precision(self.handle))
-        return [k for k, x in self.PRECISIONS.items() if x == v][0]
+        return 'fp64' if v == 0 else 'fp16x3'
 
     def last_kernel_ms(self):
         ms = ctypes.c_float()

@@ -907,7 +907,7 @@ extern "C" int32_t sctda_bin_cluster(sctda_ctx* ctx, int32_t G, const double* d_
     // that the contraction of batch i+1 (caller's stream) overlaps the MST / selection kernels of
     // batch i (the context's auxiliary stream): the few largest patches bound the MST time of a
     // batch and would otherwise leave most SMs idle.
-    // opt-in 3xTF32 contraction (gemm_tf32.cu): it splits rows 0..max(member) of Xn into (hi, lo)
+    // opt-in split-precision contraction (gemm_split.cu): it splits rows 0..max(member) of Xn into (hi, lo)
     // operands once per call; reserve that workspace before the Gram buffers are sized
     int64_t x_rows = 0;
     if (ctx->precision == 1) {
@@ -920,7 +920,7 @@ extern "C" int32_t sctda_bin_cluster(sctda_ctx* ctx, int32_t G, const double* d_
         SCTDA_CUDA(ctx, cudaMemcpyAsync(&h_max, d_max, 4, cudaMemcpyDeviceToHost, st));
         SCTDA_CUDA(ctx, cudaStreamSynchronize(st));
         x_rows = (int64_t)h_max + 1;
-        if (!sctda_ws(ctx, WS_SPLIT, (size_t)x_rows * ((G + 31) / 32) * 64 * sizeof(float))) return SCTDA_ERR_NOMEM;
+        if (!sctda_ws(ctx, WS_SPLIT, (size_t)x_rows * ((G + 63) / 64) * 256 + 256)) return SCTDA_ERR_NOMEM;
     }
     size_t free_b = 0, total_b = 0;
     SCTDA_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));

@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(256) row_normalize_kernel(const double* __rest
 
 // bulk: the rows are zero-padded to a multiple of 16 columns (ldx >= roundup16(G)), every K stage is full
 int launch_gemm(sctda_ctx* ctx, const GemmArgs& a, int64_t tiles_hint, cudaStream_t st, bool bulk, bool reuse_split = false) {
-    if (ctx->precision == 1 && a.nrows > 0) return sctda_launch_gemm_tf32(ctx, a, st, reuse_split);   // opt-in 3xTF32 (gemm_tf32.cu)
+    if (ctx->precision == 1 && a.nrows > 0) return sctda_launch_gemm_split(ctx, a, st, reuse_split);   // opt-in 3xTF32 (gemm_split.cu)
     if (!(ctx->attr_done & 2u)) {
         SCTDA_CUDA(ctx, cudaFuncSetAttribute(gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
         SCTDA_CUDA(ctx, cudaFuncSetAttribute(gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));

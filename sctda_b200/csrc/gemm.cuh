@@ -1,5 +1,5 @@
 // Problem description shared by the two contraction kernels: the FP64 DMMA kernel (dist.cu, the
-// default, bit-exact against the oracle) and the opt-in 3xTF32 tcgen05 kernel (gemm_tf32.cu).
+// default, bit-exact against the oracle) and the opt-in 3xTF32 tcgen05 kernel (gemm_split.cu).
 #pragma once
 #include "common.cuh"
 
@@ -34,6 +34,6 @@ struct GemmArgs {
 };
 
 
-// gemm_tf32.cu: same problems, 3xTF32 on the tcgen05 tensor cores (sctda_set_precision(ctx, 1)).
+// gemm_split.cu: same problems, 3xTF32 on the tcgen05 tensor cores (sctda_set_precision(ctx, 1)).
 // reuse_split: the (hi, lo) operands of this X are already in the workspace (later batches of one call).
-int sctda_launch_gemm_tf32(sctda_ctx* ctx, const GemmArgs& a, cudaStream_t st, bool reuse_split);
+int sctda_launch_gemm_split(sctda_ctx* ctx, const GemmArgs& a, cudaStream_t st, bool reuse_split);

@@ -1,30 +1,33 @@
-// Hot path (a), stage 1, OPT-IN precision: the cells x cells Gram / distance contraction as
-// 3xTF32 on the 5th-generation tensor cores (tcgen05.mma kind::tf32, accumulators in TMEM).
+// Hot path (a), stage 1, OPT-IN precision: the cells x cells Gram / distance contraction as three
+// half-precision tensor-core products on the 5th-generation tensor cores (tcgen05.mma kind::f16,
+// fp32 accumulators in TMEM) -- the "3xTF32" idea with FP16 containers.
 //
 // BASELINE.json north_star (1): "... an opt-in FP32/3xTF32 mode at a stated <= 1e-5 relative
 // tolerance".  The default stays the FP64 DMMA kernel of dist.cu (bit-exact against the oracle);
 // sctda_set_precision(ctx, 1) routes the same problems (patch Gram tiles for the clustering of
 // /root/reference/scTDA/main.py:768-771, distance row blocks for the MDS lens of :746-751) here.
 //
-// Arithmetic.  Every normalised value x (float64) is split once into two TF32 numbers,
-//     hi = tf32(x),  lo = tf32(x - hi)            (22 significand bits between them)
-// and  x.y ~= hi.hi' + (hi.lo' + lo.hi')  -- three tensor-core products, the dropped lo.lo' term is
+// Arithmetic.  TF32 and FP16 both carry 11 significant bits; FP16 does it in half the bytes and at
+// twice the tensor-core rate, and its narrow exponent range is handled by power-of-two scaling
+// (exact).  With s = 2^e chosen so that max|x| s is in [2^14, 2^15), every value is split once into
+//     hi = fp16(x s),   lo = fp16((x s - hi) 2^11)           (22 significant bits between them)
+// and  x.y s^2 ~= hi.hi' + 2^-11 (hi.lo' + lo.hi')  -- three products, the dropped lo.lo' term is
 // 2^-22 relative.  The large and the small products accumulate in SEPARATE fp32 TMEM accumulators
-// (so the cross terms are not absorbed by the rounding of the big sum) and are added in float64 in
-// the epilogue, which then applies the same Gram / euclidean / correlation epilogue as dist.cu.
+// and are combined in float64 in the epilogue, which then applies the same Gram / euclidean /
+// correlation epilogue as dist.cu.
 //
-// fp32 accumulation in the tensor core truncates: over K = 5,000 (625 accumulation steps) a single
-// accumulator drifts by 4e-5 (measured).  The K loop is therefore cut into SEGMENTS of 256 features
+// fp32 accumulation in the tensor core truncates: over K = 5,000 a single accumulator drifts by
+// 4e-5 (measured with TF32 operands).  The K loop is therefore cut into SEGMENTS of 512 features
 // that alternate between the two TMEM accumulator stages; the epilogue warps drain each finished
-// segment into float64 register sums while the next segment's MMAs run (measured error: see the
-// header, sctda_set_precision).
+// segment into float64 register sums while the next segment's MMAs run (measured error: see
+// sctda_set_precision in the header).
 //
 // Kernel (sm_100a), persistent, one CTA per SM, 352 threads in three roles:
 //   warps 8-9  producers: gather operand rows (index lists: a tiled TMA box cannot express them)
 //              with 16-byte cp.async into the canonical K-major SWIZZLE_128B layout the UMMA
-//              shared-memory descriptors expect, 3-stage ring of 64 KB (K = 32 per stage:
+//              shared-memory descriptors expect, 3-stage ring of 64 KB (K = 64 per stage:
 //              A_hi, A_lo, B_hi, B_lo blocks of 128 rows x 128 bytes);
-//   warp 10    one elected thread issues tcgen05.mma: per K = 8 step
+//   warp 10    one elected thread issues tcgen05.mma: per K = 16 step
 //                  D[:, 0:256)   += A_hi . [B_hi ; B_lo]^T     (M128 N256: hi.hi and hi.lo in one issue)
 //                  D[:, 128:256) += A_lo . B_hi^T             (M128 N128)
 //              and tcgen05.commit releases the stage / publishes the accumulator;
@@ -32,8 +35,9 @@
 //              tcgen05.ld + float64 accumulation of both accumulators (64 sums per thread), at the
 //              end of the tile the epilogue transform and direct + mirrored (symmetric) float64 stores.
 // TMEM: 2 accumulator stages x 256 columns = all 512 columns, so draining segment s overlaps the
-// MMAs of segment s+1 (also across tiles).  Every mbarrier wait is bounded (trap after ~4 s) so a protocol bug
-// cannot hang the device.
+// MMAs of segment s+1 (also across tiles).  Every mbarrier wait is bounded (trap after ~4 s) so a
+// protocol bug cannot hang the device.
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -41,20 +45,22 @@
 
 namespace {
 
-constexpr int TM = 128, TN = 128, KC = 32;
+constexpr int TM = 128, TN = 128, KC = 64;                  // K elements per stage: 128-byte rows of fp16
 constexpr int T_STAGES = 3, LAG = 2;
-constexpr int BLK_BYTES = TM * KC * 4;                  // 16 KB, one swizzled 128-row block
+constexpr int BLK_BYTES = TM * KC * 2;                  // 16 KB, one swizzled 128-row block
 constexpr int STAGE_BYTES = 4 * BLK_BYTES;              // A_hi, A_lo, B_hi, B_lo
 constexpr int EPI_THREADS = 256, PROD_THREADS = 64, MMA_WARP = (EPI_THREADS + PROD_THREADS) / 32;
 constexpr int T_THREADS = EPI_THREADS + PROD_THREADS + 32;
-constexpr int SEG = 8;                                  // K chunks (256 features) per fp32 accumulation segment
+constexpr int SEG = 8;                                  // K chunks (512 features) per fp32 accumulation segment
+constexpr double LO_SCALE = 2048.0;                     // 2^11, applied to the residual before it is rounded to fp16
 constexpr size_t T_SMEM = (size_t)T_STAGES * STAGE_BYTES + 1024;
 constexpr int ACC_COLS = 256;                           // fp32 columns per accumulator stage
 
 struct TArgs {
     GemmArgs g;
-    const uint4* Xs;        // split operands: [row][kchunk][hi 32 floats | lo 32 floats]
-    int kchunks;            // ceil(G / 32)
+    const uint4* Xs;        // split operands: [row][kchunk][hi 64 halfs | lo 64 halfs]
+    int kchunks;            // ceil(G / 64)
+    const float* scale;     // device scalar: the power of two s applied before the split
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -94,15 +100,15 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
-// kind::tf32, fp32 accumulate, A and B K-major, M = 128
+// kind::f16 with FP16 operands (format 0), fp32 accumulate, A and B K-major, M = 128
 __device__ __forceinline__ constexpr uint32_t umma_idesc(int n) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+    return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
 }
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -174,7 +180,7 @@ __device__ __forceinline__ int64_t total_tiles(const GemmArgs& a) {
     return a.tile_prefix[a.nprob];
 }
 
-__global__ void __launch_bounds__(T_THREADS, 1) gemm_tf32x3_kernel(TArgs ta) {
+__global__ void __launch_bounds__(T_THREADS, 1) gemm_split3_kernel(TArgs ta) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar_full[T_STAGES], bar_empty[T_STAGES], bar_tfull[2], bar_tempty[2];
     __shared__ uint32_t tmem_base_s;
@@ -257,12 +263,12 @@ __global__ void __launch_bounds__(T_THREADS, 1) gemm_tf32x3_kernel(TArgs ta) {
                         tc_fence_after();
                         const uint32_t base = smem0 + s * STAGE_BYTES;
 #pragma unroll
-                        for (int k = 0; k < KC / 8; ++k) {
+                        for (int k = 0; k < KC / 16; ++k) {
                             const uint64_t a_hi = umma_desc(base + k * 32);
                             const uint64_t a_lo = umma_desc(base + BLK_BYTES + k * 32);
                             const uint64_t b_hl = umma_desc(base + 2 * BLK_BYTES + k * 32);
-                            umma_tf32(d, a_hi, b_hl, idesc256, (kb > k0 || k > 0) ? 1u : 0u);
-                            umma_tf32(d + 128, a_lo, b_hl, idesc128, 1u);
+                            umma_f16(d, a_hi, b_hl, idesc256, (kb > k0 || k > 0) ? 1u : 0u);
+                            umma_f16(d + 128, a_lo, b_hl, idesc128, 1u);
                         }
                         umma_commit(bar_empty + s);                     // the stage is free when these MMAs have read it
                     }
@@ -275,6 +281,8 @@ __global__ void __launch_bounds__(T_THREADS, 1) gemm_tf32x3_kernel(TArgs ta) {
         // ---------------- epilogue: float64 running sums over the K segments ----------------
         uint32_t segcount = 0;
         const int quarter = warp & 3, half = warp >> 2;                 // TMEM lanes 32*quarter.., columns 64*half..
+        const double sc = (double)*ta.scale;
+        const double unscale = 1.0 / (sc * sc);                        // exact: s is a power of two
         for (int64_t t = blockIdx.x; t < total; t += gridDim.x) {
             const Tile tl = decode_tile(a, t);
             double acc[64];
@@ -294,7 +302,7 @@ __global__ void __launch_bounds__(T_THREADS, 1) gemm_tf32x3_kernel(TArgs ta) {
                     tmem_ld_wait();
 #pragma unroll
                     for (int j = 0; j < 16; ++j)
-                        acc[c * 16 + j] += (double)__uint_as_float(big[j]) + (double)__uint_as_float(small[j]);
+                        acc[c * 16 + j] += (double)__uint_as_float(big[j]) + (double)__uint_as_float(small[j]) * (1.0 / LO_SCALE);
                 }
                 tc_fence_before();
                 mbar_arrive(bar_tempty + as);
@@ -308,7 +316,7 @@ __global__ void __launch_bounds__(T_THREADS, 1) gemm_tf32x3_kernel(TArgs ta) {
 #pragma unroll
                 for (int j = 0; j < 64; ++j) {
                     if (c0 + j >= tl.pr.nb) continue;
-                    double v = acc[j];
+                    double v = acc[j] * unscale;
                     if (a.epilogue != EPI_GRAM) {
                         const int64_t gc = tl.pr.rows_b ? (int64_t)tl.pr.rows_b[c0 + j] : (int64_t)(tl.pr.row0_b + c0 + j);
                         if (a.epilogue == EPI_EUCLID) v = sqrt(fmax(fma(-2.0, v, sqr + a.sq[gc]), 0.0));
@@ -329,52 +337,86 @@ __global__ void __launch_bounds__(T_THREADS, 1) gemm_tf32x3_kernel(TArgs ta) {
     }
 }
 
-// x -> (tf32(x), tf32(x - tf32(x))), laid out [row][K chunk of 32][hi 32 | lo 32], zero padded in K
-__global__ void __launch_bounds__(256) split_tf32_kernel(const double* __restrict__ X, int64_t ldx, int64_t nrows, int G,
-                                                         int kchunks, float* __restrict__ Xs) {
-    const int64_t per_row = (int64_t)kchunks * 32;
+// max |x| over the table as float bits (non-negative floats order like unsigned integers)
+__global__ void __launch_bounds__(256) absmax_kernel(const double* __restrict__ X, int64_t ldx, int64_t nrows, int G,
+                                                     unsigned* __restrict__ out) {
+    const int64_t total = nrows * (int64_t)G;
+    float m = 0.f;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = e / G;
+        m = fmaxf(m, fabsf((float)X[row * ldx + (e - row * G)]));
+    }
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));
+}
+
+// scale[0] = 2^e with max|x| 2^e in [2^14, 2^15)  (1 for an all-zero table)
+__global__ void scale_kernel(const unsigned* __restrict__ absmax, float* __restrict__ scale) {
+    const float m = __uint_as_float(*absmax);
+    int e = 0;
+    if (m > 0.f && isfinite(m)) {
+        frexpf(m, &e);                                  // m = f 2^e, f in [0.5, 1)
+        e = 15 - e;
+    }
+    scale[0] = ldexpf(1.f, max(min(e, 100), -100));
+}
+
+// x -> (fp16(x s), fp16((x s - hi) 2^11)), laid out [row][K chunk of 64][hi 64 | lo 64], zero padded in K
+__global__ void __launch_bounds__(256) split_fp16_kernel(const double* __restrict__ X, int64_t ldx, int64_t nrows, int G,
+                                                         int kchunks, const float* __restrict__ scale, __half* __restrict__ Xs) {
+    const int64_t per_row = (int64_t)kchunks * KC;
     const int64_t total = nrows * per_row;
+    const double s = (double)*scale;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
         const int64_t row = e / per_row;
         const int k = (int)(e - row * per_row);
-        const double x = k < G ? X[row * ldx + k] : 0.0;
-        uint32_t hi, lo;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"((float)x));
-        const double rest = x - (double)__uint_as_float(hi);
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"((float)rest));
-        float* dst = Xs + row * per_row * 2 + (int64_t)(k >> 5) * 64 + (k & 31);
-        dst[0] = __uint_as_float(hi);
-        dst[32] = __uint_as_float(lo);
+        const double x = k < G ? X[row * ldx + k] * s : 0.0;
+        const __half hi = __double2half(x);
+        const __half lo = __double2half((x - (double)__half2float(hi)) * LO_SCALE);
+        __half* dst = Xs + row * per_row * 2 + (int64_t)(k / KC) * (2 * KC) + (k % KC);
+        dst[0] = hi;
+        dst[KC] = lo;
     }
 }
 
 }  // namespace
 
-int sctda_launch_gemm_tf32(sctda_ctx* ctx, const GemmArgs& a, cudaStream_t st, bool reuse_split) {
-    if (a.nrows <= 0) return sctda_fail(ctx, SCTDA_ERR_UNSUPPORTED, "3xTF32 contraction: the row count of X is unknown%s");
+int sctda_launch_gemm_split(sctda_ctx* ctx, const GemmArgs& a, cudaStream_t st, bool reuse_split) {
+    if (a.nrows <= 0) return sctda_fail(ctx, SCTDA_ERR_UNSUPPORTED, "split-precision contraction: the row count of X is unknown%s");
     const int kchunks = (a.G + KC - 1) / KC;
     if ((double)a.nrows * kchunks * 16.0 >= 4294967296.0)
-        return sctda_fail(ctx, SCTDA_ERR_UNSUPPORTED, "3xTF32 contraction: operand too large for 32-bit row offsets%s");
+        return sctda_fail(ctx, SCTDA_ERR_UNSUPPORTED, "split-precision contraction: operand too large for 32-bit row offsets%s");
     if (!(ctx->attr_done & 64u)) {
-        SCTDA_CUDA(ctx, cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T_SMEM));
+        SCTDA_CUDA(ctx, cudaFuncSetAttribute(gemm_split3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T_SMEM));
         ctx->attr_done |= 64u;
     }
-    float* Xs = (float*)sctda_ws(ctx, WS_SPLIT, (size_t)a.nrows * kchunks * 64 * sizeof(float));
-    if (!Xs) return SCTDA_ERR_NOMEM;
-    const int64_t elems = a.nrows * (int64_t)kchunks * 32;
+    // workspace: the split operands (4 bytes per element) followed by the scale and the max scratch
+    const size_t xs_bytes = (size_t)a.nrows * kchunks * 2 * KC * sizeof(__half);
+    unsigned char* wsp = (unsigned char*)sctda_ws(ctx, WS_SPLIT, xs_bytes + 256);
+    if (!wsp) return SCTDA_ERR_NOMEM;
+    __half* Xs = (__half*)wsp;
+    float* d_scale = (float*)(wsp + xs_bytes);
+    unsigned* d_absmax = (unsigned*)(wsp + xs_bytes + 64);
+    const int64_t elems = a.nrows * (int64_t)kchunks * KC;
     int64_t sgrid = cdiv64(elems, 256);
     if (sgrid > (int64_t)ctx->sm_count * 16) sgrid = (int64_t)ctx->sm_count * 16;
     if (!reuse_split) {
-        split_tf32_kernel<<<(unsigned)sgrid, 256, 0, st>>>(a.X, a.ldx, a.nrows, a.G, kchunks, Xs);
-        SCTDA_LAUNCH_CHECK(ctx, "split_tf32_kernel");
+        SCTDA_CUDA(ctx, cudaMemsetAsync(d_absmax, 0, 4, st));
+        absmax_kernel<<<(unsigned)sgrid, 256, 0, st>>>(a.X, a.ldx, a.nrows, a.G, d_absmax);
+        SCTDA_LAUNCH_CHECK(ctx, "absmax_kernel");
+        scale_kernel<<<1, 1, 0, st>>>(d_absmax, d_scale);
+        SCTDA_LAUNCH_CHECK(ctx, "scale_kernel");
+        split_fp16_kernel<<<(unsigned)sgrid, 256, 0, st>>>(a.X, a.ldx, a.nrows, a.G, kchunks, d_scale, Xs);
+        SCTDA_LAUNCH_CHECK(ctx, "split_fp16_kernel");
     }
     TArgs ta;
     ta.g = a;
     ta.Xs = (const uint4*)Xs;
     ta.kchunks = kchunks;
+    ta.scale = d_scale;
     SCTDA_TIME_BEGIN(ctx, st);
-    gemm_tf32x3_kernel<<<(unsigned)ctx->sm_count, T_THREADS, T_SMEM, st>>>(ta);
+    gemm_split3_kernel<<<(unsigned)ctx->sm_count, T_THREADS, T_SMEM, st>>>(ta);
     SCTDA_TIME_END(ctx, st);
-    SCTDA_LAUNCH_CHECK(ctx, "gemm_tf32x3_kernel");
+    SCTDA_LAUNCH_CHECK(ctx, "gemm_split3_kernel");
     return SCTDA_OK;
 }

@@ -83,7 +83,7 @@ def pairwise_distances(ctx, Xd, metric, row_block=8192):
     D = torch.empty((n, n), dtype=torch.float64, device=dev)
     code = {'euclidean': 0, 'correlation': 1}[metric]
     if ctx.get_precision() != 'fp64':
-        row_block = n                 # the 3xTF32 path splits the operands once per call
+        row_block = n                 # the split-precision path splits the operands once per call
     for r0 in range(0, n, row_block):
         r1 = min(n, r0 + row_block)
         ctx.check(ctx.lib.sctda_pairdist_rows_f64(ctx.handle, n, g, _lib.ptr(Xn), int(Xn.stride(0)), _lib.ptr(sq), r0, r1,
@@ -460,7 +460,7 @@ def mapper_graph(df, lens_data, resolution=10, gain=0.5, equalize=True, clust='a
     G networkx.Graph with nodes 0..V-1 and weight-1.0 edges, all_clusters[k] the ascending row
     positions of node k, patches {(i, j): row positions of cover patch (i, j)}.
     `metric` (extension): distances used by the per-patch clustering.
-    `precision` (extension): 'fp64' (default, graph identical to the oracle) or '3xtf32' (opt-in
+    `precision` (extension): 'fp64' (default, graph identical to the oracle) or 'fp16x3' (opt-in
     tcgen05 contraction, distances within 1e-5; see include/sctda_b200.h sctda_set_precision)."""
     import networkx
     if clust != 'agglomerative':

@@ -1,4 +1,4 @@
-"""Opt-in 3xTF32 contraction (tcgen05) against the FP64 DMMA kernel: error of the distance
+"""Opt-in split-precision (fp16x3) tcgen05 contraction against the FP64 DMMA kernel: error of the distance
 matrix, contraction time and the Mapper graph at a given shape.
 
     python tools/tf32_probe.py [cells genes metric resolution gain]
@@ -29,20 +29,20 @@ def main():
     ctx.set_kernel_timing(True)
     nd = min(n, 8192)
     D = {}
-    for mode in ('fp64', '3xtf32'):
+    for mode in ('fp64', 'fp16x3'):
         with ctx.precision(mode):
             for _ in range(2):
                 D[mode] = mapper.pairwise_distances(ctx, Xd[:nd], metric)
             torch.cuda.synchronize()
             out['pairdist_ms_' + mode] = ctx.last_kernel_ms()
-    err = (D['fp64'] - D['3xtf32']).abs()
+    err = (D['fp64'] - D['fp16x3']).abs()
     out['pairdist_max_abs_err'] = float(err.max())
     out['pairdist_max_rel_err'] = float((err / D['fp64'].clamp_min(1e-300))[D['fp64'] > 0].max())
     out['pairdist_mean'] = float(D['fp64'].mean())
     del D, err
     lens = mapper.pca_lens_device(Xd).cpu().numpy()
     res = {}
-    for mode in ('fp64', '3xtf32'):
+    for mode in ('fp64', 'fp16x3'):
         with ctx.precision(mode):
             for _ in range(2):
                 prof = {}
@@ -55,7 +55,7 @@ def main():
             out['build_ms_' + mode] = e0.elapsed_time(e1)
             out['gemm_ms_' + mode] = ctx.last_kernel_ms()
             out['profile_' + mode] = {k: round(v, 3) for k, v in prof.items() if isinstance(v, (int, float))}
-    a, b = res['fp64'], res['3xtf32']
+    a, b = res['fp64'], res['fp16x3']
     out['V'] = [int(a.V), int(b.V)]
     out['E'] = [int(a.E), int(b.E)]
     out['labels_identical'] = bool(a.labels.shape == b.labels.shape and (a.labels == b.labels).all())
