@@ -46,7 +46,7 @@
 namespace {
 
 constexpr int TM = 128, TN = 128, KC = 64;                  // K elements per stage: 128-byte rows of fp16
-constexpr int T_STAGES = 3, LAG = 2;
+constexpr int T_STAGES = 3;
 constexpr int BLK_BYTES = TM * KC * 2;                  // 16 KB, one swizzled 128-row block
 constexpr int STAGE_BYTES = 4 * BLK_BYTES;              // A_hi, A_lo, B_hi, B_lo
 constexpr int EPI_THREADS = 256, PROD_THREADS = 64, MMA_WARP = (EPI_THREADS + PROD_THREADS) / 32;
@@ -139,6 +139,7 @@ struct Tile {
     GemmProblem pr;
     int ti, tj;
     bool mirror;
+    bool diag;      // diagonal tile of a patch Gram: the B rows ARE the A rows, only A is staged
 };
 
 // tile t of the launch -> problem and tile coordinates (same enumeration as dist.cu: a single
@@ -151,6 +152,7 @@ __device__ __forceinline__ Tile decode_tile(const GemmArgs& a, int64_t t) {
         o.ti = (int)(t / tn);
         o.tj = (int)(t % tn);
         o.mirror = false;
+        o.diag = false;
         return o;
     }
     int lo = 0, hi = a.nprob;
@@ -167,6 +169,7 @@ __device__ __forceinline__ Tile decode_tile(const GemmArgs& a, int64_t t) {
     o.ti = ti;
     o.tj = ti + (int)lt;
     o.mirror = o.ti != o.tj;
+    o.diag = !o.mirror;
     o.pr.rows_a = o.pr.rows_b = a.members + a.bin_off[bin];
     o.pr.row0_a = o.pr.row0_b = 0;
     o.pr.na = o.pr.nb = m;
@@ -231,26 +234,24 @@ __global__ void __launch_bounds__(T_THREADS, 1) gemm_split3_kernel(TArgs ta) {
                 const uint4* src = ta.Xs + kb * 16;
 #pragma unroll
                 for (int i = 0; i < NR; ++i) {
+                    if (i >= NR / 2 && tl.diag) break;                  // diagonal tile: B = A
                     const int rr = rsub + RSTEP * (i % (NR / 2));       // row within the 128-row block
                     cp_async_16(dst + (i / (NR / 2)) * (2 * BLK_BYTES) + rr * 128 + (((piece & 7) ^ (rr & 7)) << 4), src + roff[i]);
                 }
-                cp_async_commit();
-                if (it >= LAG) {
-                    cp_async_wait<LAG>();
-                    fence_proxy_async();
-                    mbar_arrive(bar_full + (it - LAG) % T_STAGES);
-                }
+                // asynchronous arrival: the barrier is signalled when this thread's copies have landed, the
+                // thread itself moves on to the next stage (waiting here would serialise issue and MMA)
+                asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar_full + s)) : "memory");
             }
         }
-        // drain: the last LAG stages
-        if (it >= 2) { cp_async_wait<1>(); fence_proxy_async(); mbar_arrive(bar_full + (it - 2) % T_STAGES); }
-        if (it >= 1) { cp_async_wait<0>(); fence_proxy_async(); mbar_arrive(bar_full + (it - 1) % T_STAGES); }
+        cp_async_commit();
+        cp_async_wait<0>();
     } else if (warp == MMA_WARP) {
         // ---------------- MMA issuer ----------------
         if (lane == 0) {
             uint32_t it = 0, segcount = 0;
             const uint32_t idesc256 = umma_idesc(256), idesc128 = umma_idesc(128);
             for (int64_t t = blockIdx.x; t < total; t += gridDim.x) {
+                const uint32_t b_off = decode_tile(a, t).diag ? 0u : 2u * BLK_BYTES;   // [B_hi ; B_lo] = [A_hi ; A_lo] on the diagonal
                 for (int k0 = 0; k0 < kchunks; k0 += SEG, ++segcount) {
                     const uint32_t as = segcount & 1;
                     mbar_wait(bar_tempty + as, ((segcount >> 1) & 1) ^ 1);
@@ -266,7 +267,7 @@ __global__ void __launch_bounds__(T_THREADS, 1) gemm_split3_kernel(TArgs ta) {
                         for (int k = 0; k < KC / 16; ++k) {
                             const uint64_t a_hi = umma_desc(base + k * 32);
                             const uint64_t a_lo = umma_desc(base + BLK_BYTES + k * 32);
-                            const uint64_t b_hl = umma_desc(base + 2 * BLK_BYTES + k * 32);
+                            const uint64_t b_hl = umma_desc(base + b_off + k * 32);
                             umma_f16(d, a_hi, b_hl, idesc256, (kb > k0 || k > 0) ? 1u : 0u);
                             umma_f16(d + 128, a_lo, b_hl, idesc128, 1u);
                         }

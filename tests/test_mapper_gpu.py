@@ -364,3 +364,85 @@ def test_smacof_matches_sklearn():
                                                  normalized_stress=False)
     assert s1 == pytest.approx(ref_s, rel=1e-6)
     numpy.testing.assert_allclose(pos1.cpu().numpy(), ref_pos, rtol=1e-5, atol=1e-7)
+
+
+# ---- opt-in split-precision contraction (tcgen05, sctda_set_precision(ctx, 1)) ---------------------
+
+SPLIT_TOL = 1e-5            # the tolerance include/sctda_b200.h states for precision mode 1
+
+
+@pytest.mark.parametrize('shape', [(300, 77), (129, 64), (1000, 1000), (2500, 333), (64, 5000)])
+@pytest.mark.parametrize('metric', ['correlation', 'euclidean'])
+def test_split_precision_distances_within_stated_tolerance(shape, metric):
+    """Gram entries within 1e-5 of the FP64 kernel relative to |x||y| (correlation: rows are unit
+    vectors, so absolute 1e-5 on 1 - r; euclidean: on the squared distance over |x|^2 + |y|^2)."""
+    from sctda_b200 import mapper
+    ctx = _gpu()
+    n, g = shape
+    X, _ = _data(n, g, seed=3 * n + g)
+    X[n // 3] = X[n // 3 + 1]                                  # duplicate rows: distance exactly 0 on the diagonal only
+    Xd = mapper._padded_device_table(X, torch.device('cuda', 0))
+    D0 = mapper.pairwise_distances(ctx, Xd, metric)
+    with ctx.precision('fp16x3'):
+        assert ctx.get_precision() == 'fp16x3'
+        D1 = mapper.pairwise_distances(ctx, Xd, metric)
+    assert ctx.get_precision() == 'fp64'
+    assert torch.isfinite(D1).all()
+    assert (torch.diagonal(D1) == 0).all()
+    if metric == 'correlation':
+        err = (D1 - D0).abs().max().item()
+    else:
+        sq = (Xd * Xd).sum(dim=1)
+        err = ((D1 * D1 - D0 * D0).abs() / (sq[:, None] + sq[None, :]).clamp_min(1e-300)).max().item()
+    assert err <= SPLIT_TOL, err
+    assert err > 0.0                                           # it really is the other kernel
+
+
+@pytest.mark.parametrize('scale', [2.0 ** -40, 1.0, 3.0e7])
+def test_split_precision_is_scale_invariant(scale):
+    """The power-of-two pre-scaling keeps the FP16 operands in range whatever the units of the table."""
+    from sctda_b200 import mapper
+    ctx = _gpu()
+    X, _ = _data(400, 150, seed=5)
+    Xd = mapper._padded_device_table(X * scale, torch.device('cuda', 0))
+    D0 = mapper.pairwise_distances(ctx, Xd, 'euclidean')
+    with ctx.precision('3xtf32'):                              # the north star's name is accepted as an alias
+        D1 = mapper.pairwise_distances(ctx, Xd, 'euclidean')
+    sq = (Xd * Xd).sum(dim=1)
+    err = ((D1 * D1 - D0 * D0).abs() / (sq[:, None] + sq[None, :]).clamp_min(1e-300)).max().item()
+    assert err <= SPLIT_TOL, err
+    Z = torch.zeros((130, 40), dtype=torch.float64, device='cuda')
+    with ctx.precision('fp16x3'):
+        assert (mapper.pairwise_distances(ctx, Z, 'euclidean') == 0).all()
+
+
+def test_split_precision_graph_and_mode_handling():
+    """The graph build in the opt-in mode: same cover (it does not depend on the contraction),
+    node count and labels equal to the FP64 build on this data set except where a near-tie in the
+    linkage order flips (none here; the mode does not GUARANTEE identity); gram_gather stays FP64."""
+    from sctda_b200 import _lib, mapper
+    ctx = _gpu()
+    X, lens = _data(3000, 400, seed=11)
+    Xd = mapper._padded_device_table(X, torch.device('cuda', 0))
+    a = mapper.build_graph_device(ctx, Xd, lens, 12, 3.0, metric='correlation')
+    with ctx.precision('fp16x3'):
+        b = mapper.build_graph_device(ctx, Xd, lens, 12, 3.0, metric='correlation')
+        rows = torch.arange(0, 200, dtype=torch.int32, device='cuda')
+        Xn, _ = mapper.row_normalize(ctx, Xd, 'correlation')
+        g1 = mapper.gram_gather(ctx, Xn, rows, rows)
+    g0 = mapper.gram_gather(ctx, Xn, rows, rows)
+    assert (g0 == g1).all()                                    # sctda_gram_gather_f64 is always FP64
+    assert (a.bin_off == b.bin_off).all() and (a.members == b.members).all()
+    same_K = (a.bin_K == b.bin_K).float().mean().item()
+    assert same_K >= 0.99, same_K
+    assert abs(int(a.V) - int(b.V)) <= max(1, int(a.V) // 100)
+    with pytest.raises(ValueError):
+        ctx.set_precision('fp8')
+    assert ctx.lib.sctda_set_precision(ctx.handle, 7) == -4
+    assert ctx.get_precision() == 'fp64'
+    # single-feature and tiny problems go through the same kernel
+    x1 = mapper._padded_device_table(numpy.arange(1.0, 10.0).reshape(9, 1), torch.device('cuda', 0))
+    with ctx.precision('fp16x3'):
+        d = mapper.pairwise_distances(ctx, x1, 'euclidean').cpu().numpy()
+    ref = numpy.abs(numpy.arange(1.0, 10.0)[:, None] - numpy.arange(1.0, 10.0)[None, :])
+    assert numpy.abs(d - ref).max() <= 1e-3                    # sqrt of a 1e-5-relative squared distance near 0
