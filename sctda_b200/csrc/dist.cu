@@ -218,6 +218,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(GemmArgs a) {
     }
     if (a.nprob == 0) {
         const int tn = (a.single.nb + BN - 1) / BN;
+        if (a.symmetric) {                                    // square and symmetric: upper triangle of tiles, mirrored
+            const int64_t total = (int64_t)tn * (tn + 1) / 2;
+            for (int64_t t = blockIdx.x; t < total; t += gridDim.x) {
+                int64_t lt = t;
+                int ti = 0;
+                while (lt >= tn - ti) { lt -= tn - ti; ++ti; }
+                gemm_tile<BULK>(a, a.single, ti, ti + (int)lt, smem, lt != 0, bars, it);
+            }
+            return;
+        }
         const int64_t total = (int64_t)((a.single.na + BM - 1) / BM) * tn;
         for (int64_t t = blockIdx.x; t < total; t += gridDim.x)
             gemm_tile<BULK>(a, a.single, (int)(t / tn), (int)(t % tn), smem, false, bars, it);
@@ -377,5 +387,8 @@ extern "C" int32_t sctda_pairdist_rows_f64(sctda_ctx* ctx, int32_t N, int32_t G,
     a.epilogue = metric == 0 ? EPI_EUCLID : EPI_CORR;
     a.single.row0_a = r0; a.single.na = r1 - r0; a.single.row0_b = 0; a.single.nb = N;
     a.single.out = d_D; a.single.ldo = ldd;
-    return launch_gemm(ctx, a, cdiv64(r1 - r0, BM) * cdiv64(N, BN), (cudaStream_t)stream, ldxn >= ((int64_t)G + 15) / 16 * 16);
+    a.symmetric = (r0 == 0 && r1 == N) ? 1 : 0;              // the whole matrix: half the tiles, mirrored (bit-identical: products commute)
+    const int64_t q = cdiv64(N, BN);
+    return launch_gemm(ctx, a, a.symmetric ? q * (q + 1) / 2 : cdiv64(r1 - r0, BM) * q, (cudaStream_t)stream,
+                       ldxn >= ((int64_t)G + 15) / 16 * 16);
 }

@@ -24,6 +24,7 @@ struct GemmArgs {
     int epilogue;
     // single problem (nprob == 0) or batched patches
     GemmProblem single;
+    int symmetric;               // single problem with rows_a == rows_b, na == nb: upper-triangular tiles, mirrored
     int nprob;
     const int32_t* prob_bin;     // [nprob] patch index of problem p
     const int32_t* bin_off;      // member offsets of all patches

@@ -149,6 +149,16 @@ __device__ __forceinline__ Tile decode_tile(const GemmArgs& a, int64_t t) {
     if (a.nprob == 0) {
         const int tn = (a.single.nb + TN - 1) / TN;
         o.pr = a.single;
+        if (a.symmetric) {
+            int64_t lt = t;
+            int ti = 0;
+            while (lt >= tn - ti) { lt -= tn - ti; ++ti; }
+            o.ti = ti;
+            o.tj = ti + (int)lt;
+            o.mirror = lt != 0;
+            o.diag = lt == 0;
+            return o;
+        }
         o.ti = (int)(t / tn);
         o.tj = (int)(t % tn);
         o.mirror = false;
@@ -179,7 +189,10 @@ __device__ __forceinline__ Tile decode_tile(const GemmArgs& a, int64_t t) {
 }
 
 __device__ __forceinline__ int64_t total_tiles(const GemmArgs& a) {
-    if (a.nprob == 0) return (int64_t)((a.single.na + TM - 1) / TM) * ((a.single.nb + TN - 1) / TN);
+    if (a.nprob == 0) {
+        const int64_t tn = (a.single.nb + TN - 1) / TN;
+        return a.symmetric ? tn * (tn + 1) / 2 : (int64_t)((a.single.na + TM - 1) / TM) * tn;
+    }
     return a.tile_prefix[a.nprob];
 }
 

@@ -74,16 +74,18 @@ def row_normalize(ctx, Xd, metric):
     return buf[:, :g], sq
 
 
-def pairwise_distances(ctx, Xd, metric, row_block=8192):
-    """The N x N dissimilarity of apply_lens(lens='mds', metric=...) (ref:746-751), computed
-    row block by row block on the device."""
+def pairwise_distances(ctx, Xd, metric, row_block=None):
+    """The N x N dissimilarity of apply_lens(lens='mds', metric=...) (ref:746-751) on the device.
+    One call over all rows computes the upper triangle of tiles and mirrors it (bit-identical:
+    products commute); `row_block` computes it row block by row block instead (the sharding unit
+    of SURVEY.md §8e: independent row blocks against all columns)."""
     dev = Xd.device
     Xn, sq = row_normalize(ctx, Xd, metric)
     n, g = Xn.shape
     D = torch.empty((n, n), dtype=torch.float64, device=dev)
     code = {'euclidean': 0, 'correlation': 1}[metric]
-    if ctx.get_precision() != 'fp64':
-        row_block = n                 # the split-precision path splits the operands once per call
+    if row_block is None or ctx.get_precision() != 'fp64':
+        row_block = max(n, 1)         # (the split-precision path splits the operands once per call)
     for r0 in range(0, n, row_block):
         r1 = min(n, r0 + row_block)
         ctx.check(ctx.lib.sctda_pairdist_rows_f64(ctx.handle, n, g, _lib.ptr(Xn), int(Xn.stride(0)), _lib.ptr(sq), r0, r1,

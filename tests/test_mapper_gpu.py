@@ -89,6 +89,9 @@ def test_pairdist_rows(metric):
     assert (_bits(D) == _bits(ref)).all()
     numpy.testing.assert_allclose(D, ssd.cdist(X, X, metric), rtol=1e-9, atol=1e-7)
     assert (numpy.diag(D) == 0.0).all()
+    # one call over all rows: upper triangle of tiles, mirrored -- the same bits
+    Ds = mapper.pairwise_distances(ctx, Xd, metric).cpu().numpy()
+    assert (_bits(Ds) == _bits(ref)).all()
 
 
 def _device_result(ctx, X, lens, r, gain, equalize=True, metric='euclidean', max_K=5, stat='db'):
