@@ -39,17 +39,28 @@ __global__ void __launch_bounds__(ST) smacof_row_kernel(int N, const double* __r
     const double2 zi = Z[i];
     const double* drow = D + (int64_t)i * ldd;
     double sr = 0.0, sx = 0.0, sy = 0.0, st = 0.0, sd = 0.0;
+#pragma unroll 4
     for (int j = threadIdx.x; j < N; j += ST) {
         const double2 zj = __ldg(Z + j);
         const double dx = zi.x - zj.x, dy = zi.y - zj.y;
         const double d2 = dx * dx + dy * dy;
-        double dist = (j == i) ? 0.0 : sqrt(d2);
         const double delta = __ldg(drow + j);
+        // 1/sqrt(d2) from the single-precision estimate and two Newton steps (full double accuracy):
+        // the generic sqrt + divide sequences made this bandwidth-bound pass FP64-issue-bound
+        double dist, r;
+        if (j != i && d2 > 1e-30 && d2 < 1e30) {
+            double y = (double)rsqrtf((float)d2);
+            y = y * fma(-0.5 * d2, y * y, 1.5);
+            y = y * fma(-0.5 * d2, y * y, 1.5);
+            dist = d2 * y;
+            r = delta * y;
+        } else {
+            dist = (j == i) ? 0.0 : sqrt(d2);
+            r = delta / (dist == 0.0 ? 1e-5 : dist);          // sklearn: distances[distances == 0] = 1e-5
+        }
         const double e = dist - delta;
         st += e * e;
         sd += (j == i) ? 0.0 : d2;
-        if (dist == 0.0) dist = 1e-5;                       // sklearn: distances[distances == 0] = 1e-5
-        const double r = delta / dist;
         sr += r;
         sx += r * zj.x;
         sy += r * zj.y;

@@ -23,6 +23,11 @@ D = mapper.pairwise_distances(ctx, X, metric)
 torch.cuda.synchronize()
 t1 = time.perf_counter()
 print('pairwise %s distances %d x %d x %d: %.1f ms, %.2f TFLOP/s' % (metric, N, N, G, 1e3 * (t1 - t0), 2.0 * N * N * G / (t1 - t0) / 1e12))
+t_a = time.perf_counter()
+pos, stress, it = mapper.smacof_device(ctx, D, max_iter=5, random_state=0, return_n_iter=True)
+torch.cuda.synchronize()
+print('5-iteration run: %.1f ms' % (1e3 * (time.perf_counter() - t_a)))
+t1 = time.perf_counter()
 pos, stress, it = mapper.smacof_device(ctx, D, max_iter=max_iter, random_state=0, return_n_iter=True)
 torch.cuda.synchronize()
 t2 = time.perf_counter()
