@@ -211,11 +211,11 @@ __global__ void __launch_bounds__(256) prim_kernel(ClusterArgs a) {
 // Prim with the keys in REGISTERS: 512 threads, thread t owns vertices t, t+512, ... (KPT of them);
 // |row|^2 and the parents live in shared memory.  One barrier per step (double-buffered warp
 // results); the only serial latency left is the fetch of the next row of the Gram tile.
-template <int KPT>
-__global__ void __launch_bounds__(512) prim_reg_kernel(ClusterArgs a) {
+template <int KPT, int NT>
+__global__ void __launch_bounds__(NT) prim_reg_kernel(ClusterArgs a) {
     extern __shared__ __align__(16) unsigned char s_raw[];
-    __shared__ double s_rk[2][16];
-    __shared__ int s_ri[2][16];
+    __shared__ double s_rk[2][NT / 32];
+    __shared__ int s_ri[2][NT / 32];
     const int prob = a.prob0 + blockIdx.x;
     const int b = a.prob_bin[prob];
     const int off = a.bin_off[b], m = a.bin_off[b + 1] - off;
@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(512) prim_reg_kernel(ClusterArgs a) {
     double key[KPT];
 #pragma unroll
     for (int i = 0; i < KPT; ++i) {
-        const int q = tid + 512 * i;
+        const int q = tid + NT * i;
         key[i] = (q < m && q != 0) ? INFINITY : -1.0;          // -1: in the tree (or not a vertex)
         if (q < m) { gpp[q] = Gm[(int64_t)q * m + q]; par[q] = -1; }
     }
@@ -238,12 +238,12 @@ __global__ void __launch_bounds__(512) prim_reg_kernel(ClusterArgs a) {
         const double* row = Gm + (int64_t)u * m;
         double g[KPT];
 #pragma unroll
-        for (int i = 0; i < KPT; ++i) g[i] = key[i] >= 0.0 ? row[tid + 512 * i] : 0.0;
+        for (int i = 0; i < KPT; ++i) g[i] = key[i] >= 0.0 ? row[tid + NT * i] : 0.0;
         double bk = INFINITY;
         int bi = 0x7fffffff;
 #pragma unroll
         for (int i = 0; i < KPT; ++i) {
-            const int q = tid + 512 * i;
+            const int q = tid + NT * i;
             double k = key[i];
             if (k >= 0.0) {
                 const double d = dist2(gu, gpp[q], g[i]);
@@ -263,13 +263,13 @@ __global__ void __launch_bounds__(512) prim_reg_kernel(ClusterArgs a) {
         bk = s_rk[pp][0];
         bi = s_ri[pp][0];
 #pragma unroll
-        for (int w = 1; w < 16; ++w) {
+        for (int w = 1; w < NT / 32; ++w) {
             const double ok = s_rk[pp][w];
             const int oi = s_ri[pp][w];
             if (ok < bk || (ok == bk && oi < bi)) { bk = ok; bi = oi; }
         }
         u = bi;
-        const int sel = (u & 511) == tid ? (u >> 9) : -1;
+        const int sel = (u % NT) == tid ? (u / NT) : -1;
 #pragma unroll
         for (int i = 0; i < KPT; ++i) key[i] = (sel == i) ? -1.0 : key[i];     // stays in registers
         if (sel >= 0) {
@@ -950,16 +950,20 @@ extern "C" int32_t sctda_bin_cluster(sctda_ctx* ctx, int32_t G, const double* d_
     if (!(ctx->attr_done & 1u)) {
         SCTDA_CUDA(ctx, cudaFuncSetAttribute(prim_cluster_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024 - 1024));
         SCTDA_CUDA(ctx, cudaFuncSetAttribute(prim_cluster_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 136 * 1024));
-        SCTDA_CUDA(ctx, cudaFuncSetAttribute(prim_reg_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        SCTDA_CUDA(ctx, cudaFuncSetAttribute(prim_reg_kernel<8, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         SCTDA_CUDA(ctx, cudaFuncSetAttribute(labels_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
         ctx->attr_done |= 1u;
     }
     // size classes of the MST kernels (a test hook lowers them so that small inputs reach every kernel)
-    int thr_mid = 4096, thr_big = 16384, thr_huge = 28000;
+    int thr_mid = 4096, thr_big = 16384, thr_huge = 28000, thr_1k = 1024, thr_512 = 512;
     if (const char* e = getenv("SCTDA_TEST_PRIM_THRESHOLDS")) {
-        int x = 0, y = 0, z = 0;
-        if (sscanf(e, "%d,%d,%d", &x, &y, &z) == 3 && 0 < x && x <= y && y <= z && x <= 4096 && y <= 16384 && z <= 28000) {
+        int x = 0, y = 0, z = 0, p = 0, q = 0;
+        const int got = sscanf(e, "%d,%d,%d,%d,%d", &x, &y, &z, &p, &q);
+        if (got >= 3 && 0 < x && x <= y && y <= z && x <= 4096 && y <= 16384 && z <= 28000) {
             thr_mid = x; thr_big = y; thr_huge = z;
+            thr_1k = thr_1k < x ? thr_1k : x;
+            thr_512 = thr_512 < x ? thr_512 : x;
+            if (got == 5 && 0 < q && q <= p && p <= x && p <= 1024 && q <= 512) { thr_1k = p; thr_512 = q; }
         }
     }
     if (!ctx->aux_stream) {
@@ -1035,12 +1039,14 @@ extern "C" int32_t sctda_bin_cluster(sctda_ctx* ctx, int32_t G, const double* d_
         // MST: patches are sorted by size; [0,n_huge) above 28,000 cells (generic kernel, state in
         // global memory), [n_huge,n_big) above 16,384 and [n_big,n_mid) above 4,096 (one cluster of 8
         // CTAs per patch, 8 or 4 register keys per thread), the rest one CTA with 8 register keys
-        int n_huge = 0, n_big = 0, n_mid = 0;
+        int n_huge = 0, n_big = 0, n_mid = 0, n_1k = 0, n_512 = 0;
         for (size_t j = bt.pos; j < bt.end; ++j) {
             const int m = h_off[order[j] + 1] - h_off[order[j]];
             if (m > thr_huge) ++n_huge;
             if (m > thr_big) ++n_big;
             if (m > thr_mid) ++n_mid;
+            if (m > thr_1k) ++n_1k;
+            if (m > thr_512) ++n_512;
         }
         if (n_huge) {
             a.prob0 = 0;
@@ -1059,11 +1065,25 @@ extern "C" int32_t sctda_bin_cluster(sctda_ctx* ctx, int32_t G, const double* d_
             prim_cluster_kernel<4><<<(n_mid - n_big) * kClusterCtas, 512, (size_t)mm * 8 + 16, aux_st>>>(a);
             SCTDA_LAUNCH_CHECK(ctx, "prim_cluster_kernel<4>");
         }
-        if (nb > n_mid) {
+        // one CTA per patch, keys in registers; small patches get small CTAs so that many of them share
+        // an SM (each step is one dependent row fetch: throughput comes from patches in flight)
+        if (n_1k > n_mid) {
             a.prob0 = n_mid;
             const int mm = h_off[order[bt.pos + n_mid] + 1] - h_off[order[bt.pos + n_mid]];
-            prim_reg_kernel<8><<<nb - n_mid, 512, (size_t)mm * 12 + 16, aux_st>>>(a);
-            SCTDA_LAUNCH_CHECK(ctx, "prim_reg_kernel<8>");
+            prim_reg_kernel<8, 512><<<n_1k - n_mid, 512, (size_t)mm * 12 + 16, aux_st>>>(a);
+            SCTDA_LAUNCH_CHECK(ctx, "prim_reg_kernel<8,512>");
+        }
+        if (n_512 > n_1k) {
+            a.prob0 = n_1k;
+            const int mm = h_off[order[bt.pos + n_1k] + 1] - h_off[order[bt.pos + n_1k]];
+            prim_reg_kernel<4, 256><<<n_512 - n_1k, 256, (size_t)mm * 12 + 16, aux_st>>>(a);
+            SCTDA_LAUNCH_CHECK(ctx, "prim_reg_kernel<4,256>");
+        }
+        if (nb > n_512) {
+            a.prob0 = n_512;
+            const int mm = h_off[order[bt.pos + n_512] + 1] - h_off[order[bt.pos + n_512]];
+            prim_reg_kernel<4, 128><<<nb - n_512, 128, (size_t)mm * 12 + 16, aux_st>>>(a);
+            SCTDA_LAUNCH_CHECK(ctx, "prim_reg_kernel<4,128>");
         }
         a.prob0 = 0;
         labels_kernel<<<nb, kSelThreads, (size_t)bt.max_lev * (max_K - 1) + 16, aux_st>>>(a);

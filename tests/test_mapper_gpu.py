@@ -298,16 +298,16 @@ def test_mapper_abi_errors_and_empty_inputs():
 
 
 def test_every_mst_kernel_gives_the_same_graph(monkeypatch):
-    """The four MST kernels (one CTA with register keys, clusters of 8 CTAs with 4 / 8 keys per
-    thread, the generic global-memory kernel) are selected by patch size; the test hook lowers the
-    size classes so that one small input reaches all of them, and the graph must not change."""
+    """The MST kernels (one CTA of 128 / 256 / 512 threads with register keys, clusters of 8 CTAs with
+    4 / 8 keys per thread, the generic global-memory kernel) are selected by patch size; the test hook
+    lowers the size classes so that one small input reaches all of them, and the graph must not change."""
     from oracle import mapper_oracle as mo
     ctx = _gpu()
     X, lens = _data(900, 32, seed=77)
     edges, clusters, _ = mo.mapper_graph(X, lens, 3, 0.8)
     sizes = sorted(len(p) for p in mo.cover(lens, 3, 0.8)[0])
     assert sizes[0] < 120 and sizes[-1] > 330
-    for thr in (None, '150,250,400', '100,200,300', '60,61,62'):
+    for thr in (None, '150,250,400', '100,200,300', '60,61,62', '400,500,600,250,150', '330,400,500,200,120'):
         if thr is None:
             monkeypatch.delenv('SCTDA_TEST_PRIM_THRESHOLDS', raising=False)
         else:

@@ -1,4 +1,4 @@
-"""Runs only the Mapper build at a given size (profiling helper): python tools/mapper_run.py N G r gain metric [reps]"""
+"""Runs only the Mapper build at a given size (profiling helper): python tools/mapper_run.py N G r gain metric [reps] [fp64|fp16x3]"""
 import json
 import os
 import sys
@@ -13,6 +13,8 @@ reps = int(sys.argv[6]) if len(sys.argv) > 6 else 2
 dev = torch.device('cuda', 0)
 ctx = _lib.context(0)
 ctx.set_kernel_timing(True)
+if len(sys.argv) > 7:
+    ctx.set_precision(sys.argv[7])
 X = synth.expression_genes_torch(G, N, seed=synth.SEED + 11, device=dev).T.contiguous()
 lens = mapper.pca_lens_device(X)
 for _ in range(reps):
