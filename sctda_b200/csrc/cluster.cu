@@ -296,8 +296,8 @@ __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(512) prim
     extern __shared__ __align__(16) unsigned char s_raw[];
     __shared__ double s_rk[16];
     __shared__ int s_ri[16];
-    __shared__ double s_ck[2];                   // this CTA's candidate of step parity 0 / 1
-    __shared__ int s_ci[2];
+    __shared__ __align__(16) unsigned long long s_slot[2][kClusterCtas][2];   // candidates (key bits, index) of all CTAs, by step parity
+    __shared__ __align__(8) unsigned long long s_xbar[2];                      // their arrival barriers
     const int rank = (int)cluster.block_rank();
     const int prob = a.prob0 + blockIdx.x / kClusterCtas;
     const int b = a.prob_bin[prob];
@@ -317,7 +317,18 @@ __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(512) prim
         par[i] = -1;
     }
     if (gt == 0) { a.mst_parent[off] = -1; a.mst_w[off] = 0.0; a.mst_order[off] = -1; a.mst_seq[off] = 0; }
-    __syncthreads();
+    if (tid == 0) {
+        for (int i = 0; i < 2; ++i)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(&s_xbar[i])) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    cluster.sync();                               // every CTA's barriers exist before anybody sends
+    unsigned slot_remote[kClusterCtas], xbar_remote[kClusterCtas];       // shared::cluster addresses (used by thread 0)
+#pragma unroll
+    for (int r = 0; r < kClusterCtas; ++r) {
+        asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(slot_remote[r]) : "r"((unsigned)__cvta_generic_to_shared(&s_slot[0][rank][0])), "r"(r));
+        asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(xbar_remote[r]) : "r"((unsigned)__cvta_generic_to_shared(&s_xbar[0])), "r"(r));
+    }
     int u = 0;
     for (int t = 0; t < m - 1; ++t) {
         const double gu = gpp[u];
@@ -355,15 +366,39 @@ __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(512) prim
                 const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
                 if (ok < bk || (ok == bk && oi < bi)) { bk = ok; bi = oi; }
             }
-            if (lane == 0) { s_ck[pp] = bk; s_ci[pp] = bi; }
+            if (lane == 0) {
+                // Candidate exchange without a cluster barrier: one 16-byte st.async into slot [pp][rank] of
+                // every CTA (this one included), each completing 16 bytes on the receiver's mbarrier; every
+                // CTA then waits on its OWN barrier for the 128 bytes of the step.  (barrier.cluster with
+                // release semantics costs a MEMBAR.ALL.GPU per step: 30 % of this kernel's stall samples.)
+                const unsigned xb = (unsigned)__cvta_generic_to_shared(&s_xbar[pp]);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(xb), "r"(16u * kClusterCtas) : "memory");
+                const unsigned long long kb = (unsigned long long)__double_as_longlong(bk), ib = (unsigned long long)(unsigned)bi;
+#pragma unroll
+                for (int r = 0; r < kClusterCtas; ++r)
+                    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b64 [%0], {%1, %2}, [%3];"
+                                 ::"r"(slot_remote[r] + (unsigned)pp * (kClusterCtas * 16)), "l"(kb), "l"(ib),
+                                   "r"(xbar_remote[r] + (unsigned)pp * 8) : "memory");
+            }
         }
-        cluster.sync();                           // candidates of all CTAs are published
+        {
+            const unsigned xb = (unsigned)__cvta_generic_to_shared(&s_xbar[pp]);
+            const unsigned parity = (unsigned)(t >> 1) & 1u;
+            const long long t0 = clock64();
+            for (;;) {
+                unsigned ok;
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                             : "=r"(ok) : "r"(xb), "r"(parity) : "memory");
+                if (ok) break;
+                if (clock64() - t0 > 8000000000LL) __trap();
+            }
+        }
         bk = INFINITY;
         bi = 0x7fffffff;
 #pragma unroll
         for (int r = 0; r < kClusterCtas; ++r) {
-            const double ok = *cluster.map_shared_rank(&s_ck[pp], r);
-            const int oi = *cluster.map_shared_rank(&s_ci[pp], r);
+            const double ok = __longlong_as_double((long long)s_slot[pp][r][0]);
+            const int oi = (int)s_slot[pp][r][1];
             if (ok < bk || (ok == bk && oi < bi)) { bk = ok; bi = oi; }
         }
         u = bi;
