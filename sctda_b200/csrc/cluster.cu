@@ -991,6 +991,7 @@ extern "C" int32_t sctda_bin_cluster(sctda_ctx* ctx, int32_t G, const double* d_
     }
     // size classes of the MST kernels (a test hook lowers them so that small inputs reach every kernel)
     int thr_mid = 4096, thr_big = 16384, thr_huge = 28000, thr_1k = 1024, thr_512 = 512;
+    bool split_small = false;                     // separate launches with small CTAs for small patches (test hook only)
     if (const char* e = getenv("SCTDA_TEST_PRIM_THRESHOLDS")) {
         int x = 0, y = 0, z = 0, p = 0, q = 0;
         const int got = sscanf(e, "%d,%d,%d,%d,%d", &x, &y, &z, &p, &q);
@@ -998,7 +999,7 @@ extern "C" int32_t sctda_bin_cluster(sctda_ctx* ctx, int32_t G, const double* d_
             thr_mid = x; thr_big = y; thr_huge = z;
             thr_1k = thr_1k < x ? thr_1k : x;
             thr_512 = thr_512 < x ? thr_512 : x;
-            if (got == 5 && 0 < q && q <= p && p <= x && p <= 1024 && q <= 512) { thr_1k = p; thr_512 = q; }
+            if (got == 5 && 0 < q && q <= p && p <= x && p <= 1024 && q <= 512) { thr_1k = p; thr_512 = q; split_small = true; }
         }
     }
     if (!ctx->aux_stream) {
@@ -1100,21 +1101,25 @@ extern "C" int32_t sctda_bin_cluster(sctda_ctx* ctx, int32_t G, const double* d_
             prim_cluster_kernel<4><<<(n_mid - n_big) * kClusterCtas, 512, (size_t)mm * 8 + 16, aux_st>>>(a);
             SCTDA_LAUNCH_CHECK(ctx, "prim_cluster_kernel<4>");
         }
-        // one CTA per patch, keys in registers; small patches get small CTAs so that many of them share
-        // an SM (each step is one dependent row fetch: throughput comes from patches in flight)
-        if (n_1k > n_mid) {
+        // One CTA of 512 threads per patch, keys in registers, ONE launch for every patch up to 4,096 cells:
+        // the launch lasts as long as the dependent chain of its largest patch, and the small patches
+        // fill the other SMs meanwhile.  (Measured: separate launches with 128 / 256-thread CTAs for the
+        // small patches run those 3x faster but serialise behind the large-patch launch: 7.4 -> 9.5 ms at
+        // config 2; the smaller instantiations stay available through the test hook.)
+        if (n_1k > n_mid || (nb > n_mid && !split_small)) {
             a.prob0 = n_mid;
+            const int last = split_small ? n_1k : nb;
             const int mm = h_off[order[bt.pos + n_mid] + 1] - h_off[order[bt.pos + n_mid]];
-            prim_reg_kernel<8, 512><<<n_1k - n_mid, 512, (size_t)mm * 12 + 16, aux_st>>>(a);
+            prim_reg_kernel<8, 512><<<last - n_mid, 512, (size_t)mm * 12 + 16, aux_st>>>(a);
             SCTDA_LAUNCH_CHECK(ctx, "prim_reg_kernel<8,512>");
         }
-        if (n_512 > n_1k) {
+        if (split_small && n_512 > n_1k) {
             a.prob0 = n_1k;
             const int mm = h_off[order[bt.pos + n_1k] + 1] - h_off[order[bt.pos + n_1k]];
             prim_reg_kernel<4, 256><<<n_512 - n_1k, 256, (size_t)mm * 12 + 16, aux_st>>>(a);
             SCTDA_LAUNCH_CHECK(ctx, "prim_reg_kernel<4,256>");
         }
-        if (nb > n_512) {
+        if (split_small && nb > n_512) {
             a.prob0 = n_512;
             const int mm = h_off[order[bt.pos + n_512] + 1] - h_off[order[bt.pos + n_512]];
             prim_reg_kernel<4, 128><<<nb - n_512, 128, (size_t)mm * 12 + 16, aux_st>>>(a);
