@@ -1002,6 +1002,10 @@ extern "C" int32_t sctda_bin_cluster(sctda_ctx* ctx, int32_t G, const double* d_
             if (got == 5 && 0 < q && q <= p && p <= x && p <= 1024 && q <= 512) { thr_1k = p; thr_512 = q; split_small = true; }
         }
     }
+    if (!ctx->fork_stream) {
+        SCTDA_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->fork_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) SCTDA_CUDA(ctx, cudaEventCreateWithFlags(&ctx->fork_ev[i], cudaEventDisableTiming));
+    }
     if (!ctx->aux_stream) {
         SCTDA_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
         for (int i = 0; i < 4; ++i) SCTDA_CUDA(ctx, cudaEventCreateWithFlags(&ctx->pipe_ev[i], cudaEventDisableTiming));
@@ -1084,6 +1088,16 @@ extern "C" int32_t sctda_bin_cluster(sctda_ctx* ctx, int32_t G, const double* d_
             if (m > thr_1k) ++n_1k;
             if (m > thr_512) ++n_512;
         }
+        // The cluster launches (few SMs, long dependent chains) and the one-CTA launch (all other patches)
+        // run side by side: fork the latter onto a second stream, join before the selection kernels.
+        static const bool no_fork = getenv("SCTDA_NO_FORK") && atoi(getenv("SCTDA_NO_FORK")) != 0;
+        const bool fork = !no_fork && n_mid > 0 && nb > n_mid;
+        cudaStream_t reg_st = aux_st;
+        if (fork) {
+            SCTDA_CUDA(ctx, cudaEventRecord(ctx->fork_ev[0], aux_st));
+            SCTDA_CUDA(ctx, cudaStreamWaitEvent(ctx->fork_stream, ctx->fork_ev[0], 0));
+            reg_st = ctx->fork_stream;
+        }
         if (n_huge) {
             a.prob0 = 0;
             prim_kernel<<<n_huge, 256, 16, aux_st>>>(a);
@@ -1110,20 +1124,24 @@ extern "C" int32_t sctda_bin_cluster(sctda_ctx* ctx, int32_t G, const double* d_
             a.prob0 = n_mid;
             const int last = split_small ? n_1k : nb;
             const int mm = h_off[order[bt.pos + n_mid] + 1] - h_off[order[bt.pos + n_mid]];
-            prim_reg_kernel<8, 512><<<last - n_mid, 512, (size_t)mm * 12 + 16, aux_st>>>(a);
+            prim_reg_kernel<8, 512><<<last - n_mid, 512, (size_t)mm * 12 + 16, reg_st>>>(a);
             SCTDA_LAUNCH_CHECK(ctx, "prim_reg_kernel<8,512>");
         }
         if (split_small && n_512 > n_1k) {
             a.prob0 = n_1k;
             const int mm = h_off[order[bt.pos + n_1k] + 1] - h_off[order[bt.pos + n_1k]];
-            prim_reg_kernel<4, 256><<<n_512 - n_1k, 256, (size_t)mm * 12 + 16, aux_st>>>(a);
+            prim_reg_kernel<4, 256><<<n_512 - n_1k, 256, (size_t)mm * 12 + 16, reg_st>>>(a);
             SCTDA_LAUNCH_CHECK(ctx, "prim_reg_kernel<4,256>");
         }
         if (split_small && nb > n_512) {
             a.prob0 = n_512;
             const int mm = h_off[order[bt.pos + n_512] + 1] - h_off[order[bt.pos + n_512]];
-            prim_reg_kernel<4, 128><<<nb - n_512, 128, (size_t)mm * 12 + 16, aux_st>>>(a);
+            prim_reg_kernel<4, 128><<<nb - n_512, 128, (size_t)mm * 12 + 16, reg_st>>>(a);
             SCTDA_LAUNCH_CHECK(ctx, "prim_reg_kernel<4,128>");
+        }
+        if (fork) {
+            SCTDA_CUDA(ctx, cudaEventRecord(ctx->fork_ev[1], ctx->fork_stream));
+            SCTDA_CUDA(ctx, cudaStreamWaitEvent(aux_st, ctx->fork_ev[1], 0));
         }
         a.prob0 = 0;
         labels_kernel<<<nb, kSelThreads, (size_t)bt.max_lev * (max_K - 1) + 16, aux_st>>>(a);

@@ -23,6 +23,8 @@ struct sctda_ctx {
     unsigned attr_done;                  // per-context (= per-device) one-time kernel attribute setup, one bit per file
     cudaStream_t aux_stream;             // second stream for the patch pipeline (cluster.cu)
     cudaEvent_t pipe_ev[4];
+    cudaStream_t fork_stream;            // MST size classes run side by side (cluster.cu)
+    cudaEvent_t fork_ev[2];
     int precision;                       // sctda_set_precision: 0 = FP64 (bit-exact, default), 1 = 3xTF32 contraction
 };
 

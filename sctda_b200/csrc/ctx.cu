@@ -43,6 +43,10 @@ extern "C" int32_t sctda_ctx_destroy(sctda_ctx* ctx) {
     for (int i = 0; i < 4; ++i)
         if (ctx->pipe_ev[i]) cudaEventDestroy(ctx->pipe_ev[i]);
     if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
+    if (ctx->fork_stream) {
+        cudaStreamDestroy(ctx->fork_stream);
+        for (int i = 0; i < 2; ++i) cudaEventDestroy(ctx->fork_ev[i]);
+    }
     free(ctx);
     return SCTDA_OK;
 }
