@@ -438,6 +438,29 @@ __device__ __forceinline__ double masked_seq_sum(const double* __restrict__ v, i
     return acc;
 }
 
+// The same sum by one WARP: lane l loads element p0 + l of each 32-element chunk (coalesced, two
+// chunks ahead of the adds), the chunk is then added in element order through shuffles.  Every lane
+// ends with the same value.  Masked and out-of-range terms add +0.0 (exact no-ops), so the result
+// equals masked_seq_sum bit for bit; what changes is that the m dependent adds no longer wait for
+// m/8 global-memory round trips.
+__device__ __forceinline__ double warp_masked_seq_sum(const double* __restrict__ v, int stride, const int8_t* lab, int I, int m,
+                                                      int lane) {
+    auto fetch = [&](int p0) -> double {
+        const int p = p0 + lane;
+        return (p < m && lab[p] == I) ? v[(int64_t)p * stride] : 0.0;
+    };
+    double acc = 0.0;
+    double x0 = fetch(0), x1 = fetch(32);
+    for (int p0 = 0; p0 < m; p0 += 32) {
+        const double x2 = fetch(p0 + 64);
+#pragma unroll
+        for (int u = 0; u < 32; ++u) acc = __dadd_rn(acc, __shfl_sync(0xffffffffu, x0, u));
+        x0 = x1;
+        x1 = x2;
+    }
+    return acc;
+}
+
 constexpr int kSelThreads = 1024;
 
 // Kernel A of the selection: the (K_max - 1) heaviest tree edges and the labels of every level
@@ -554,44 +577,62 @@ __global__ void __launch_bounds__(kSelThreads) labels_kernel(ClusterArgs a) {
     // (d) labels of every level: thread L walks the vertices in insertion order; a vertex whose edge
     //     is among the L+1 heaviest opens a component, the others inherit their parent's (inserted
     //     earlier).  Components are then renumbered by their smallest vertex.
-    if (tid < nlev) {
-        const int L = tid;
+    __shared__ int8_t s_rank[kMaxK - 1][kMaxK];
+    if (warp == 0) {
+        // warp 0: lane L < nlev owns level L; all 32 lanes fetch the insertion sequence and the parents
+        // (two dependent gathers) 32 at a time, two chunks ahead of the walk
+        const bool own = lane < nlev;
+        const int L = own ? lane : 0;
         int8_t* lab = lev + (size_t)L * m;
-        int ncomp = 1;
-        int cmin[kMaxK];
-        cmin[0] = 0;
-        lab[0] = 0;
-        for (int t0 = 1; t0 < m; t0 += 8) {               // seq / par do not depend on the walk: fetched 8 ahead
-            int vv[8], pp[8];
+        // branch-free walk: a vertex whose edge is the g-th heaviest (g <= L) opens component g + 1, every
+        // other vertex inherits its parent's component; the smallest vertex of every component is tracked
+        // in registers.  (Component numbers are temporary: they are re-ranked by smallest vertex below.)
+        int hv[kMaxK - 1], cm[kMaxK];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) vv[u] = t0 + u < m ? seq[t0 + u] : 0;
+        for (int g = 0; g < kMaxK - 1; ++g) hv[g] = (g <= L && g < nlev) ? s_heavy[g] : -1;
 #pragma unroll
-            for (int u = 0; u < 8; ++u) pp[u] = t0 + u < m ? par[vv[u]] : 0;
+        for (int d = 0; d < kMaxK; ++d) cm[d] = 0x7fffffff;
+        cm[0] = 0;
+        if (own) lab[0] = 0;
+        int v0, p0, v1, p1;
+        { const int t = 1 + lane; v0 = t < m ? seq[t] : 0; p0 = t < m ? par[v0] : 0; }
+        { const int t = 33 + lane; v1 = t < m ? seq[t] : 0; p1 = t < m ? par[v1] : 0; }
+        for (int t0 = 1; t0 < m; t0 += 32) {
+            const int t2 = t0 + 64 + lane;
+            const int v2 = t2 < m ? seq[t2] : 0;
+            const int p2 = t2 < m ? par[v2] : 0;
+            const int cnt = min(32, m - t0);                  // warp-uniform
+            for (int u = 0; u < cnt; ++u) {
+                const int v = __shfl_sync(0xffffffffu, v0, u), pu = __shfl_sync(0xffffffffu, p0, u);
+                int c = own ? (int)lab[pu] : 0;
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                if (t0 + u >= m) break;
-                const int v = vv[u];
-                bool cut = false;
-                for (int g = 0; g <= L; ++g) cut |= (s_heavy[g] == v);
-                int c;
-                if (cut) { c = ncomp; cmin[ncomp++] = v; }
-                else { c = lab[pp[u]]; if (v < cmin[c]) cmin[c] = v; }
-                lab[v] = (int8_t)c;
+                for (int g = 0; g < kMaxK - 1; ++g) c = (hv[g] == v) ? g + 1 : c;
+#pragma unroll
+                for (int d = 0; d < kMaxK; ++d) cm[d] = (d == c) ? min(cm[d], v) : cm[d];
+                if (own) lab[v] = (int8_t)c;
+            }
+            v0 = v1; p0 = p1; v1 = v2; p1 = p2;
+        }
+        if (own) {
+            const int ncomp = L + 2;
+#pragma unroll
+            for (int c = 0; c < kMaxK; ++c) {                  // components renumbered by their smallest vertex
+                if (c < ncomp) {
+                    int rk = 0;
+#pragma unroll
+                    for (int d = 0; d < kMaxK; ++d) rk += (d < ncomp && cm[d] < cm[c]);
+                    s_rank[L][c] = (int8_t)rk;
+                    if (L == nlev - 1) s_fine_rep[rk] = cm[c];
+                }
             }
         }
-        int rank[kMaxK];
-        for (int c = 0; c < ncomp; ++c) {
-            int rk = 0;
-            for (int d = 0; d < ncomp; ++d) rk += (cmin[d] < cmin[c]);
-            rank[c] = rk;
-        }
-        for (int v = 0; v < m; ++v) lab[v] = (int8_t)rank[lab[v]];
-        if (L == nlev - 1)
-            for (int c = 0; c < ncomp; ++c) s_fine_rep[rank[c]] = cmin[c];
     }
     __syncthreads();
-    if (lev_in_smem)
-        for (int i = tid; i < nlev * m; i += kSelThreads) lev_out[i] = lev[i];
+    for (int i = tid; i < nlev * m; i += kSelThreads) {         // relabel (and copy out when the labels live in shared memory)
+        const int8_t r = s_rank[i / m][lev[i]];
+        lev[i] = r;
+        if (lev_in_smem) lev_out[i] = r;
+    }
     if (tid < kmax) a.fine_rep[(int64_t)prob * kMaxK + tid] = s_fine_rep[tid];
 }
 
@@ -658,7 +699,7 @@ __global__ void __launch_bounds__(kSelThreads) db_kernel(ClusterArgs a) {
     const int prob = a.prob0 + blockIdx.x;
     const int b = a.prob_bin[prob];
     const int off = a.bin_off[b], m = a.bin_off[b + 1] - off;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (m < 2 || a.stat == 1) return;
     const double* Gm = a.gram + a.gram_off[prob];
     const int kmax = m <= 5 ? 2 : min(m / 2, a.max_K);
@@ -690,16 +731,18 @@ __global__ void __launch_bounds__(kSelThreads) db_kernel(ClusterArgs a) {
 #pragma unroll
             for (int J = 0; J < kMaxK; ++J) TK[(int64_t)p * kMaxK + J] = tk[J];
         }
-        if (tid < K) {                                          // cluster sizes
+        if (warp < K) {                                         // cluster sizes, one warp per cluster
             int n = 0;
-            for (int p = 0; p < m; ++p) n += (lab[p] == tid);
-            s_n[tid] = (double)n;
+            for (int p = lane; p < m; p += 32) n += (lab[p] == warp);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+            if (lane == 0) s_n[warp] = (double)n;
         }
         __syncthreads();
-        if (tid < K * K) {                                      // c_I . c_J, one thread per pair
-            const int I = tid / K, J = tid % K;
-            const double acc = masked_seq_sum(TK + J, kMaxK, lab, I, m);
-            s_cc[I][J] = __ddiv_rn(acc, __dmul_rn(s_n[I], s_n[J]));
+        for (int pr = warp; pr < K * K; pr += kSelThreads / 32) {     // c_I . c_J, one warp per pair
+            const int I = pr / K, J = pr % K;
+            const double acc = warp_masked_seq_sum(TK + J, kMaxK, lab, I, m, lane);
+            if (lane == 0) s_cc[I][J] = __ddiv_rn(acc, __dmul_rn(s_n[I], s_n[J]));
         }
         __syncthreads();
         for (int p = tid; p < m; p += kSelThreads) {                    // |x_p - c_I|
@@ -709,7 +752,10 @@ __global__ void __launch_bounds__(kSelThreads) db_kernel(ClusterArgs a) {
             dist[p] = sqrt(d2);
         }
         __syncthreads();
-        if (tid < K) s_S[tid] = __ddiv_rn(masked_seq_sum(dist, 1, lab, tid, m), s_n[tid]);
+        if (warp < K) {
+            const double acc = warp_masked_seq_sum(dist, 1, lab, warp, m, lane);
+            if (lane == 0) s_S[warp] = __ddiv_rn(acc, s_n[warp]);
+        }
         __syncthreads();
         if (tid == 0) {
             bool any = false;
