@@ -63,9 +63,12 @@ int64_t sctda_launch_count(const sctda_ctx* ctx);
 /* Precision of the cells x cells contraction (BASELINE.json north_star (1)).
  *   0  FP64 on the DMMA tensor pipe, one fused-multiply-add chain per element: the DEFAULT, the
  *      Mapper graph is identical to the oracle's bit for bit;
- *   1  opt-in 3xTF32 on the tcgen05 tensor cores (fp32 accumulation in TMEM): Gram entries of
- *      unit-normalised rows / squared distances within 1e-5 of the FP64 result relative to
- *      |x||y| (measured: tests/test_mapper_gpu.py); the graph is NOT guaranteed identical.
+ *   1  opt-in split precision on the tcgen05 tensor cores: every value is split into two FP16
+ *      numbers (hi, scaled residual: 22 significant bits, the "3xTF32" scheme in half the bytes),
+ *      three kind::f16 products with fp32 accumulation in TMEM, drained into float64 sums every 512
+ *      features.  Gram entries of unit-normalised rows / squared distances within 1e-5 of the
+ *      FP64 result relative to |x||y| (measured <= 4e-6: tests/test_mapper_gpu.py); the graph is
+ *      NOT guaranteed identical (it was on every input of the bench and the tests).
  * Applies to sctda_bin_cluster and sctda_pairdist_rows_f64 of this context (sctda_gram_gather_f64
  * always computes in FP64).  Replaces nothing in the reference: sakmapper / sklearn compute
  * these distances in float64 (/root/reference/scTDA/main.py:746-751, 768-771). */

@@ -422,27 +422,11 @@ __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(512) prim
 // cut + Davies-Bouldin model selection per patch
 // ---------------------------------------------------------------------------------------------
 // Sum over p ascending of (lab[p] == I ? v[p*stride] : 0.0): the masked terms add +0.0, an exact
-// no-op, so this is the sequential sum over the members of cluster I; the loads do not depend on
-// the running sum and are issued eight at a time.
-__device__ __forceinline__ double masked_seq_sum(const double* __restrict__ v, int stride, const int8_t* lab, int I, int m) {
-    double acc = 0.0;
-    int p = 0;
-    for (; p + 8 <= m; p += 8) {
-        double x[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) x[u] = (lab[p + u] == I) ? v[(int64_t)(p + u) * stride] : 0.0;
-#pragma unroll
-        for (int u = 0; u < 8; ++u) acc = __dadd_rn(acc, x[u]);
-    }
-    for (; p < m; ++p) acc = __dadd_rn(acc, (lab[p] == I) ? v[(int64_t)p * stride] : 0.0);
-    return acc;
-}
-
-// The same sum by one WARP: lane l loads element p0 + l of each 32-element chunk (coalesced, two
-// chunks ahead of the adds), the chunk is then added in element order through shuffles.  Every lane
-// ends with the same value.  Masked and out-of-range terms add +0.0 (exact no-ops), so the result
-// equals masked_seq_sum bit for bit; what changes is that the m dependent adds no longer wait for
-// m/8 global-memory round trips.
+// no-op, so this is the sequential sum over the members of cluster I (oracle order).  Done by one
+// WARP: lane l loads element p0 + l of each 32-element chunk (coalesced, two chunks ahead of the
+// adds), the chunk is then added in element order through shuffles; every lane ends with the same
+// value.  The m dependent adds thus never wait for global memory (a single thread issuing eight
+// loads at a time spent m/8 round trips on it: 5.4 -> 2.2 ms on a rank of the 8-GPU build).
 __device__ __forceinline__ double warp_masked_seq_sum(const double* __restrict__ v, int stride, const int8_t* lab, int I, int m,
                                                       int lane) {
     auto fetch = [&](int p0) -> double {
