@@ -260,14 +260,18 @@ __global__ void __launch_bounds__(NT) prim_reg_kernel(ClusterArgs a) {
         const int pp = t & 1;
         if (lane == 0) { s_rk[pp][warp] = bk; s_ri[pp][warp] = bi; }
         __syncthreads();
-        bk = s_rk[pp][0];
-        bi = s_ri[pp][0];
+        // every warp reduces the NT/32 warp candidates with shuffles (log steps instead of a sequential
+        // scan by every thread; the parity double buffer makes a second barrier unnecessary)
+        bk = lane < NT / 32 ? s_rk[pp][lane] : INFINITY;
+        bi = lane < NT / 32 ? s_ri[pp][lane] : 0x7fffffff;
 #pragma unroll
-        for (int w = 1; w < NT / 32; ++w) {
-            const double ok = s_rk[pp][w];
-            const int oi = s_ri[pp][w];
+        for (int o = NT / 64; o > 0; o >>= 1) {
+            const double ok = __shfl_xor_sync(0xffffffffu, bk, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
             if (ok < bk || (ok == bk && oi < bi)) { bk = ok; bi = oi; }
         }
+        bk = __shfl_sync(0xffffffffu, bk, 0);
+        bi = __shfl_sync(0xffffffffu, bi, 0);
         u = bi;
         const int sel = (u % NT) == tid ? (u / NT) : -1;
 #pragma unroll
