@@ -397,14 +397,17 @@ __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(512) prim
                 if (clock64() - t0 > 8000000000LL) __trap();
             }
         }
-        bk = INFINITY;
-        bi = 0x7fffffff;
+        // the eight candidates, one per lane, reduced by shuffles in every warp
+        bk = lane < kClusterCtas ? __longlong_as_double((long long)s_slot[pp][lane][0]) : INFINITY;
+        bi = lane < kClusterCtas ? (int)s_slot[pp][lane][1] : 0x7fffffff;
 #pragma unroll
-        for (int r = 0; r < kClusterCtas; ++r) {
-            const double ok = __longlong_as_double((long long)s_slot[pp][r][0]);
-            const int oi = (int)s_slot[pp][r][1];
+        for (int o = kClusterCtas / 2; o > 0; o >>= 1) {
+            const double ok = __shfl_xor_sync(0xffffffffu, bk, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
             if (ok < bk || (ok == bk && oi < bi)) { bk = ok; bi = oi; }
         }
+        bk = __shfl_sync(0xffffffffu, bk, 0);
+        bi = __shfl_sync(0xffffffffu, bi, 0);
         u = bi;
         const int sel = (u % STRIDE) == gt ? (u / STRIDE) : -1;
         int pu = -1;
