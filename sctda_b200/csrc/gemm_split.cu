@@ -262,6 +262,7 @@ __global__ void __launch_bounds__(T_THREADS, 1) gemm_split3_kernel(TArgs ta) {
                     for (int kb = k0; kb < k1; ++kb, ++it) {
                         const uint32_t s = it % T_STAGES;
                         mbar_wait(bar_full + s, (it / T_STAGES) & 1);
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // cp.async wrote the stage through the generic proxy
                         tc_fence_after();
                         const uint32_t base = smem0 + s * STAGE_BYTES;
 #pragma unroll
