@@ -279,6 +279,22 @@ int32_t sctda_jsd_matrix(sctda_ctx* ctx, int32_t g, int32_t V, const double* d_P
  */
 int32_t sctda_mt19937_shuffle_rows(uint32_t* key624, int32_t* pos, int32_t rows, int32_t S, int32_t* out);
 
+/*
+ * HOST function (no GPU work): the numeric fields of a table body, i.e. the per-field float() loop
+ * of UnrootedGraph.__init__ (ref:839-885) on all host cores.  body[nbytes]: the file after its header
+ * line, rows ending in '\n' (or "\r\n"; the last row may lack it), nrows rows of ncols fields
+ * separated by the byte `sep`; strip_bar != 0 keeps only the part of a field before the first '|'
+ * (the csv variant, ref:851-853).  out[ncols][nrows] (gene-major) receives the value of every field
+ * of the plain decimal form, 0.0 for the others; those others are reported, in no particular order,
+ * as (flat field index r*ncols+c, byte offset) pairs in bad_pos[2*i], bad_pos[2*i+1] and lengths
+ * bad_len[i] for i < min(*n_bad, bad_cap) (call again with a larger capacity when *n_bad > bad_cap),
+ * so that the caller applies float() to them exactly as the reference does.  A row with a different
+ * number of fields returns SCTDA_ERR_INVALID with *bad_row = the first such row.  nthreads <= 0: all cores.
+ */
+int32_t sctda_parse_table_f64(const char* body, int64_t nbytes, int32_t sep, int32_t strip_bar, int64_t nrows,
+                              int64_t ncols, double* out, int64_t* bad_pos, int32_t* bad_len, int64_t bad_cap,
+                              int64_t* n_bad, int64_t* bad_row, int32_t nthreads);
+
 /* ---- RootedGraph root finding (first "next" row) ------------------------------- */
 /*
  * RootedGraph.get_dendrite (ref:1463-1479) for all V source nodes at once: hop distances from

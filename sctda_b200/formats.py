@@ -68,7 +68,56 @@ def _read_sidecar(path):
     return list(z['names']), numpy.ascontiguousarray(z['Y']), list(z['cell_id']), list(z['libs']), z['cdr']
 
 
-def read_table(path, shift=None, csv=False, sidecar=True):
+def _parse_native(path, csv):
+    """Header fields and the table body parsed by sctda_parse_table_f64 (all host cores):
+    (header, Y [ncol, nrow] float64, bad) with bad = [(row, col, text)] for every field the native
+    parser left to Python's float(), in row-major order.  None when the native path does not apply
+    (library not built, carriage returns in the file, empty file)."""
+    import ctypes
+    try:
+        from . import _lib
+        lib = _lib.load()
+    except (ImportError, OSError):
+        return None
+    with open(path, 'rb') as f:
+        data = f.read()
+    if not data or b'\r' in data:
+        return None
+    nl = data.find(b'\n')
+    head = data if nl < 0 else data[:nl]
+    body = b'' if nl < 0 else data[nl + 1:]
+    sep = ',' if csv else '\t'
+    header = head.decode('utf-8').split(sep)
+    if csv:
+        header = [x.split('|')[0] for x in header]
+    ncol = len(header)
+    nrow = body.count(b'\n') + (1 if body and not body.endswith(b'\n') else 0)
+    Y = numpy.empty((ncol, nrow), dtype=numpy.float64)
+    cap = max(1024, 4 * nrow)
+    while True:
+        pos = numpy.empty(2 * cap, dtype=numpy.int64)
+        ln = numpy.empty(cap, dtype=numpy.int32)
+        n_bad, bad_row = ctypes.c_int64(0), ctypes.c_int64(-1)
+        rc = lib.sctda_parse_table_f64(body, len(body), ord(sep), 1 if csv else 0, nrow, ncol, Y.ctypes.data_as(ctypes.c_void_p),
+                                       pos.ctypes.data_as(ctypes.c_void_p), ln.ctypes.data_as(ctypes.c_void_p), cap,
+                                       ctypes.byref(n_bad), ctypes.byref(bad_row), 0)
+        if rc != 0:
+            r = int(bad_row.value)
+            raise ValueError('%s: row %d does not have the %d fields of the header' % (path, r + 1 if r >= 0 else -1, ncol))
+        if n_bad.value <= cap:
+            break
+        cap = int(n_bad.value)
+    nb = int(n_bad.value)
+    flat, off = pos[0:2 * nb:2], pos[1:2 * nb:2]
+    order = numpy.argsort(flat, kind='stable')
+    bad = []
+    for i in order:
+        k, o, L = int(flat[i]), int(off[i]), int(ln[i])
+        bad.append((k // ncol, k % ncol, body[o:o + L].decode('utf-8')))
+    return header, Y, bad
+
+
+def read_table(path, shift=None, csv=False, sidecar=True, native=True):
     """ref:835-885.  Returns (names, Y, cell_id, libs, cdr):
     names   column names that become keys of dicgenes (header order),
     Y       float64 [len(names), Ncells], gene-major (one row per column of the file),
@@ -78,6 +127,9 @@ def read_table(path, shift=None, csv=False, sidecar=True):
         got = _read_sidecar(path)
         if got is not None:
             return got
+    got = _parse_native(path, csv) if native else None
+    if got is not None:
+        return _table_from_native(path, got, shift)
     sep = ',' if csv else '\t'
     with open(path, 'r') as f:
         lines = f.read().split('\n')
@@ -127,6 +179,37 @@ def read_table(path, shift=None, csv=False, sidecar=True):
             Y[k] = numpy.asarray(cols[c], dtype=numpy.float64)    # the reference float()s every field here
         cdr = numpy.zeros(0)
     return names, Y, cell_id, libs, cdr
+
+
+def _table_from_native(path, got, shift):
+    """read_table's result from the natively parsed body: the fields the parser left undecided go
+    through Python's float() exactly as ref:118-126 / ref:859-874 treat them."""
+    header, Y, bad = got
+    ncol, ncell = Y.shape
+    strings = {}                                               # col -> [(row, text)] of the non-numeric fields
+    for r, c, text in bad:
+        try:
+            Y[c, r] = float(text)
+        except ValueError:
+            strings.setdefault(c, []).append((r, text))
+    if shift is None:
+        coyt = header.index('lib') if 'lib' in header else -1
+        ttt = header.index('timepoint') if 'timepoint' in header else -1
+        cell_id = [t for _, t in strings.get(0, [])]
+        libs = [t for _, t in strings.get(coyt, [])] if coyt >= 0 else []
+        if coyt == 0:
+            cell_id = []                                       # ref:867-872: the 'lib' test comes first
+        sel = [c for c in range(ncol) if c != 0 and c != coyt and c != ttt]
+        cdr = numpy.zeros(ncell, dtype=numpy.float64)
+        for lo in range(0, len(sel), 256):                     # non-numeric fields are 0.0, hence never > 0
+            cdr += (Y[sel[lo:lo + 256]] > 0.0).sum(axis=0)
+        cdr = cdr / float(max(ncell, 1))
+        return list(header), Y, cell_id, libs, cdr
+    sel = list(range(shift, ncol)) if isinstance(shift, int) else list(numpy.arange(ncol)[shift])
+    for c in sel:
+        if c in strings:                                       # the reference float()s every field here
+            raise ValueError('could not convert string to float: %r' % (strings[c][0][1],))
+    return [header[c] for c in sel], numpy.ascontiguousarray(Y[sel]), [], [], numpy.zeros(0)
 
 
 def write_genes_tsv(path, header, rows):

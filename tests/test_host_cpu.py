@@ -167,3 +167,62 @@ def test_package_exports_the_reference_names_on_the_path():
         assert callable(getattr(scTDA, name))
     with pytest.raises(AttributeError):
         scTDA.Preprocess
+
+
+def test_native_table_parser_is_python_float(lib_path, golden_dir, tmp_path):
+    """sctda_parse_table_f64 (all host cores) against the per-field float() loop of the reference
+    (ref:859-874): same values bit for bit, same non-numeric fields, on the golden tables and on a
+    table of awkward fields."""
+    import random
+    from sctda_b200 import formats
+    for name in ('unrooted_a', 'rooted_b'):
+        path = os.path.join(golden_dir, name + '.all.tsv')
+        a = formats.read_table(path, native=True)
+        b = formats.read_table(path, native=False)
+        assert a[0] == b[0] and list(a[2]) == list(b[2]) and list(a[3]) == list(b[3])
+        assert (a[1].view(numpy.int64) == b[1].view(numpy.int64)).all()
+        numpy.testing.assert_array_equal(a[4], b[4])
+        for shift in (3, [3, 5]):
+            x, y = formats.read_table(path, shift=shift, native=True), formats.read_table(path, shift=shift, native=False)
+            assert x[0] == y[0] and (x[1].view(numpy.int64) == y[1].view(numpy.int64)).all()
+    rnd = random.Random(5)
+    rs = numpy.random.RandomState(5)
+    odd = ['', 'nan', 'inf', '-inf', ' 1.5', '1.5 ', '1_0', '0x10', '1e', 'e5', '.', '-', '+', '1.', '.5', '+.5e-3', '-0', '-0.0',
+           '1e400', '1e-400', '4.9e-324', '2.2250738585072011e-308', '17976931348623157' + '0' * 292, '0.1', '0.30000000000000004',
+           '123456789012345678901234567890', '0.000000000000000000000000000001234567890123456789', '9007199254740993',
+           '9007199254740992.5', '1E5', '1e+5', '00012', 'abc', 'D3_L_7', 'L', '1,5', '1|2', '३']
+    vals = []
+    for _ in range(3000):
+        k = rnd.randrange(6)
+        x = float(rs.standard_normal() * 10.0 ** rnd.randrange(-30, 30))
+        vals.append([repr(x), '%.12g' % x, '%d' % int(rs.randint(-10 ** 9, 10 ** 9)), '%.3e' % x, '%.25f' % (x % 1000.0),
+                     rnd.choice(odd)][k])
+    ncol = 40
+    rows = [vals[i:i + ncol] for i in range(0, len(vals) - ncol + 1, ncol)]
+    header = ['ID', 'timepoint', 'lib'] + ['g%d' % i for i in range(ncol - 3)]
+    for sep, csv, trailing in (('\t', False, True), ('\t', False, False), (',', True, True)):
+        path = str(tmp_path / ('odd%d%d.tsv' % (csv, trailing)))
+        body = [[f.replace(',', ';') for f in r] for r in rows] if csv else rows
+        with open(path, 'w', encoding='utf-8') as f:
+            f.write(sep.join(header) + '\n' + '\n'.join(sep.join(r) for r in body) + ('\n' if trailing else ''))
+        a = formats.read_table(path, csv=csv, native=True)
+        b = formats.read_table(path, csv=csv, native=False)
+        assert a[0] == b[0] and list(a[2]) == list(b[2]) and list(a[3]) == list(b[3])
+        same = (a[1].view(numpy.int64) == b[1].view(numpy.int64)) | (numpy.isnan(a[1]) & numpy.isnan(b[1]))
+        assert same.all(), numpy.argwhere(~same)[:5]
+        numpy.testing.assert_array_equal(a[4], b[4])
+    # a row with a missing / an extra field, an empty line: errors, as in the Python path
+    for bad in ('a\tb\n1\t2\n3\n', 'a\tb\n1\t2\t3\n', 'a\tb\n1\t2\n\n3\t4\n'):
+        path = str(tmp_path / 'bad.tsv')
+        with open(path, 'w') as f:
+            f.write(bad)
+        with pytest.raises(ValueError):
+            formats.read_table(path, native=True)
+        with pytest.raises(ValueError):
+            formats.read_table(path, native=False)
+    # carriage returns: the text-mode path decides (universal newlines)
+    path = str(tmp_path / 'crlf.tsv')
+    with open(path, 'wb') as f:
+        f.write(b'a\tb\r\n1\t2\r\n')
+    assert formats._parse_native(path, False) is None
+    numpy.testing.assert_array_equal(formats.read_table(path)[1], [[1.0], [2.0]])
