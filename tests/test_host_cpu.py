@@ -226,3 +226,38 @@ def test_native_table_parser_is_python_float(lib_path, golden_dir, tmp_path):
         f.write(b'a\tb\r\n1\t2\r\n')
     assert formats._parse_native(path, False) is None
     numpy.testing.assert_array_equal(formats.read_table(path)[1], [[1.0], [2.0]])
+
+
+def test_native_table_parser_fuzz(lib_path, tmp_path):
+    """Random small tables over an alphabet of digits, signs, exponents, separators and junk: the
+    native reader and the per-field float() reader agree on values, strings and on which inputs are errors."""
+    import random
+    from sctda_b200 import formats
+    rnd = random.Random(11)
+    alphabet = '0123456789.eE+- ,|_xnaif'
+    p = str(tmp_path / 'f.tsv')
+    agreed = 0
+    for _ in range(600):
+        ncol, nrow = rnd.randrange(1, 5), rnd.randrange(0, 5)
+        lines = ['\t'.join('h%d' % i for i in range(ncol))]
+        for _r in range(nrow):
+            k = ncol if rnd.random() < 0.9 else rnd.randrange(0, 6)
+            lines.append('\t'.join(''.join(rnd.choice(alphabet) for _ in range(rnd.randrange(0, 8))) for _ in range(k)))
+        with open(p, 'w') as f:
+            f.write('\n'.join(lines) + ('\n' if rnd.random() < 0.7 else ''))
+        for csv in (False, True):
+            res = []
+            for native in (True, False):
+                try:
+                    res.append(formats.read_table(p, csv=csv, native=native))
+                except ValueError:
+                    res.append(None)
+            a, b = res
+            assert (a is None) == (b is None)
+            if a is None:
+                continue
+            assert a[0] == b[0] and list(a[2]) == list(b[2]) and list(a[3]) == list(b[3]) and a[1].shape == b[1].shape
+            assert ((a[1].view(numpy.int64) == b[1].view(numpy.int64)) | (numpy.isnan(a[1]) & numpy.isnan(b[1]))).all()
+            assert numpy.array_equal(a[4], b[4], equal_nan=True)
+            agreed += 1
+    assert agreed > 500
