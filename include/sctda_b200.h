@@ -175,6 +175,28 @@ int32_t sctda_conn_perm_test(sctda_ctx* ctx, const sctda_graph* graph,
                              int32_t* d_exceed, int32_t* d_ties, double* d_scores,
                              void* stream);
 
+/*
+ * The same test for ONE shared permutation block [n, S] with the genes laid out in tiles in the
+ * order d_gene_order [G] (a permutation of 0..G-1; NULL = table order).  Results are written at the
+ * ORIGINAL gene positions, so the order never changes what is computed, only which genes share
+ * a 32-byte sector of the transposed table: the kernel never requests sectors that hold only
+ * zeros, and genes with similar supports empty more sectors (sctda_gene_order proposes an order).
+ * sctda_conn_perm_test with perm_gene_stride == 0 is this call with d_gene_order == NULL.
+ * Needs S <= 65,535 (16-bit staged permutation rows); larger graphs and per-gene permutation
+ * blocks run on the 32-gene kernel behind sctda_conn_perm_test.
+ */
+int32_t sctda_conn_perm_test_ordered(sctda_ctx* ctx, const sctda_graph* graph,
+                                     int32_t G, const double* d_Y, int64_t ldy, int32_t log2_mode,
+                                     int32_t n, const int32_t* d_perm, const int32_t* d_gene_order,
+                                     const double* d_observed, double tie_rel,
+                                     int32_t* d_exceed, int32_t* d_ties, double* d_scores,
+                                     void* stream);
+
+/* Self-test of the node epilogue: the table-driven float32(log1p(sum/q)/0.693147) with its guard
+ * against the full-accuracy path, bit for bit, on n_trials pseudo-random (sum, q) pairs.
+ * *out_slow = trials that took the full-accuracy path (may be NULL).  Synchronises the host. */
+int32_t sctda_selftest_pm_fast(sctda_ctx* ctx, int64_t n_trials, int64_t* out_mismatches, int64_t* out_slow);
+
 /* ---- hot path (a): Mapper graph build ------------------------------------------------------- */
 /*
  * The reference reaches this path through the third-party package sakmapper:

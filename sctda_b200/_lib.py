@@ -67,6 +67,9 @@ SIGNATURES = {
     'sctda_selftest_log1p': (c_i32, [c_ptr, c_i64, ctypes.POINTER(c_i64)]),
     'sctda_node_stats': (c_i32, [c_ptr, ctypes.POINTER(Graph), c_i32, c_ptr, c_i64, c_i32, c_ptr,
                                  c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
+    'sctda_conn_perm_test_ordered': (c_i32, [c_ptr, ctypes.POINTER(Graph), c_i32, c_ptr, c_i64, c_i32,
+                                             c_i32, c_ptr, c_ptr, c_ptr, c_f64, c_ptr, c_ptr, c_ptr, c_ptr]),
+    'sctda_selftest_pm_fast': (c_i32, [c_ptr, c_i64, ctypes.POINTER(c_i64), ctypes.POINTER(c_i64)]),
     'sctda_conn_perm_test': (c_i32, [c_ptr, ctypes.POINTER(Graph), c_i32, c_ptr, c_i64, c_i32,
                                      c_i32, c_ptr, c_i64, c_ptr, c_f64, c_ptr, c_ptr, c_ptr, c_ptr]),
 }

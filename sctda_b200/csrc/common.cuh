@@ -99,6 +99,12 @@ static inline void* sctda_ws(sctda_ctx* ctx, int slot, size_t bytes) {
 
 static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// conn_tile64.cu: the shared-permutation kernel on 64-gene tiles (internal entry, see conn.cu)
+bool sctda_tile64_eligible(const sctda_graph* gr);
+int sctda_conn_perm_tile64(sctda_ctx* ctx, const sctda_graph* gr, int G, const double* d_Y, int64_t ldy, int log2_mode,
+                           int n, const int32_t* d_perm, const int32_t* d_order, const double* d_observed,
+                           double tie_rel, int32_t* d_exceed, int32_t* d_ties, double* d_scores, cudaStream_t st);
+
 // Brackets the dominant kernel of a call with events when timing is on (see sctda_set_kernel_timing).
 #define SCTDA_TIME_RESET(ctx) do { if ((ctx)->timing) (ctx)->timed = 0; } while (0)
 #define SCTDA_TIME_BEGIN(ctx, st) do { if ((ctx)->timing && (ctx)->timed < 16) cudaEventRecord((ctx)->tev[2 * (ctx)->timed], st); } while (0)

@@ -1,0 +1,551 @@
+// Hot path (b), shared-permutation form of the connectivity permutation test
+// (UnrootedGraph.connectivity_pvalue, /root/reference/scTDA/main.py:966-992, "ref:"): the kernel
+// that serves sctda_conn_perm_test when one [n, S] permutation block is applied to every gene.
+//
+// Why a second kernel.  conn.cu's kernel gathers one dense 256-byte row [cell][32 genes] per
+// (node member, permutation): 8*Mtot bytes of L2 -> SM traffic per gene and permutation, and the
+// L2 -> SM fill path (about 60 B/clk/SM) is what bounds it (profiles/ncu_full_r01.txt).  Most of
+// those bytes are zeros: single-cell tables are 60-95 % zeros and a zero adds nothing to a sum.
+// This kernel keeps the reference's arithmetic and summation order bit for bit and stops moving
+// the zeros:
+//   * tiles of 64 genes, ET[tile][cell][64]; a lane owns two neighbouring genes and gathers them
+//     with ONE 16-byte load, so a 32-byte sector holds four genes of one cell;
+//   * per (tile, cell) a 16-bit sector mask says which of the sixteen sectors hold a non-zero;
+//     it travels to the lanes packed into the upper half of the composite index
+//     perm[cols[m]] (one shuffle per member, as before), and the load and the two adds of a lane
+//     are predicated on its sector's bit: sectors of zeros are never requested (adding +0.0 is
+//     the identity, so skipped members leave the sequential sum unchanged);
+//   * genes are assigned to tiles in an order that puts genes with similar supports next to
+//     each other (sctda_gene_order), which empties more sectors;
+//   * the node epilogue log1p(t)/0.693147 -> float32 (ref:983, 972) runs a short table-driven
+//     evaluation with a rigorous guard: whenever the float32 rounding could depend on the last
+//     bits, the lane falls back to the full-accuracy path of conn.cu (conn_math.cuh), so the
+//     float32 node values are those of the slow path in every case (sctda_selftest_pm_fast);
+//   * members whose whole 64-gene row is zero are dropped before the gather: a warp compacts the
+//     composite words of a node (ballot + rank, through a small shared-memory list, member order
+//     kept) while the previous node is being summed, and the sums read eight list entries at a
+//     time with two broadcast loads instead of eight shuffles.  The kernel is bound by the
+//     latency of its dependent gather rounds, so fewer rounds per node is what pays;
+//   * the permutation rows are staged as 16-bit indices (S <= 65,535), double buffered by
+//     cp.async, next to the tile's sector masks.
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "conn_math.cuh"
+
+namespace {
+
+constexpr int kT = 64;            // genes per tile
+constexpr int kPitch = 64;        // doubles per ET row
+constexpr int kChunk = 8;         // permutations per work item
+constexpr unsigned kGuard = 1u << 16;   // half-width of the ambiguity band, in units of 2^-52 of the binade
+
+__device__ double2 g_logtab[128];   // (1/c_j rounded, -log(1/c_j rounded)), c_j = 1 + (j + 1/2)/128
+
+// float32(log1p(acc/q) / 0.693147), same bits as pm_log2_value(div_rn(acc, q, inv_q)).
+// Fast evaluation: t = acc*inv_q, u = 1 + t = 2^k * m, r = m/c_j - 1 (|r| <= 2^-8),
+// log(u) = k ln2 + log c_j + r - r^2/2 + r^3/3 - r^4/4 + r^5/5; relative error of the quotient
+// below 2^-41 for t >= 2^-8 (truncation r^6/6 <= 2^-50.6 against log(u) >= 2^-8.01; every
+// rounding below 2^-52 of a term not larger than the result).  The slow path's own result is
+// within 2^-51 of the exact value, so the two float32 roundings can only differ when the fast
+// double lies within 2^-40 (relative) of a float32 rounding boundary; the guard band is 2^-36.
+__device__ __forceinline__ float pm_fast(double acc, double q, double inv_q, const double2* __restrict__ tab) {
+    const double t = acc * inv_q;
+    const double u = 1.0 + t;
+    const int hu = __double2hiint(u);
+    const int k = (hu >> 20) - 1023;
+    const double2 tc = tab[(hu >> 13) & 127];
+    const double m = __hiloint2double((hu & 0x000fffff) | 0x3ff00000, __double2loint(u));
+    const double r = fma(m, tc.x, -1.0);
+    double p = fma(r, 0.2, -0.25);
+    p = fma(r, p, 0.33333333333333331);
+    p = fma(r, p, -0.5);
+    p = fma(r, p, 1.0);
+    const double L = fma(r, p, fma((double)k, 0.69314718055994529, tc.y));
+    const double y = L * (1.0 / 0.693147);
+    const unsigned lo = (unsigned)__double2loint(y) & 0x1fffffffu;
+    const bool clear = (lo - 0x10000000u + kGuard) >= 2u * kGuard;     // away from the rounding boundary
+    float f = (float)y;
+    if (!(clear && t >= 0.00390625 && t <= 1e30)) f = pm_log2_value(div_rn(acc, q, inv_q));
+    return f;
+}
+
+struct Tile64Args {
+    int V, S, Sp, G, n, log2_mode, nchunks, tiles;
+    long long items;
+    const int32_t* node_off;
+    const int32_t* node_cols;
+    const int32_t* adj_off;
+    const int32_t* adj_idx;
+    const double* adj_w;
+    const double* ET;           // [tiles][S][kPitch], 64 used
+    const uint16_t* sec;        // [tiles][Sp]
+    const uint16_t* perm16;     // [n][Sp]
+    const int32_t* gmap;        // [tiles*64]: gene of each tile slot, -1 = padding
+    const double* inv_q;        // [V]
+    const double* observed;
+    double tie_rel;
+    int32_t* exceed;
+    int32_t* ties;
+    double* scores;
+    float* pm;                  // [grid][V][64]
+    unsigned long long* counter;
+};
+
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+
+// Eight members: the composite words of lanes l0..l0+7 of `packed` are broadcast, each lane tests
+// its sector's bit and loads its two genes under that predicate into registers cleared beforehand
+// (ptxas turns predicated FP64 adds into add + select, which costs more than the clear), then adds
+// them in member order.  The loads come first in program order.
+#define SCTDA_T64_LD(i)                                                        \
+    "and.b32 t, %" #i ", %10;\n setp.ne.u32 p, t, 0;\n"                       \
+    "shr.u32 t, %" #i ", 16;\n mad.wide.u32 ad, t, 512, %11;\n"               \
+    "mov.f64 a" #i ", 0d0000000000000000;\n mov.f64 b" #i ", 0d0000000000000000;\n" \
+    "@p ld.global.nc.v2.f64 {a" #i ", b" #i "}, [ad];\n"
+#define SCTDA_T64_ADD(i) "add.rn.f64 %0, %0, a" #i ";\nadd.rn.f64 %1, %1, b" #i ";\n"
+
+__device__ __forceinline__ void group8(double& acc0, double& acc1, const uint4 wa, const uint4 wb, unsigned lanebit,
+                                       const double* base) {
+    asm volatile(
+        "{\n.reg .pred p;\n.reg .b32 t;\n.reg .b64 ad;\n"
+        ".reg .f64 a2, a3, a4, a5, a6, a7, a8, a9, b2, b3, b4, b5, b6, b7, b8, b9;\n"
+        SCTDA_T64_LD(2) SCTDA_T64_LD(3) SCTDA_T64_LD(4) SCTDA_T64_LD(5)
+        SCTDA_T64_LD(6) SCTDA_T64_LD(7) SCTDA_T64_LD(8) SCTDA_T64_LD(9)
+        SCTDA_T64_ADD(2) SCTDA_T64_ADD(3) SCTDA_T64_ADD(4) SCTDA_T64_ADD(5)
+        SCTDA_T64_ADD(6) SCTDA_T64_ADD(7) SCTDA_T64_ADD(8) SCTDA_T64_ADD(9)
+        "}\n"
+        : "+d"(acc0), "+d"(acc1)
+        : "r"(wa.x), "r"(wa.y), "r"(wa.z), "r"(wa.w), "r"(wb.x), "r"(wb.y), "r"(wb.z), "r"(wb.w), "r"(lanebit),
+          "l"(base));
+}
+
+constexpr int kSeg = 64;          // members compacted at a time (two chunks of 32)
+constexpr int kList = kSeg + 8;   // list entries per buffer: up to 64 live members + padding to a multiple of eight
+
+// Composite word of one member: perm[col] in the high half, the sector mask of that cell in the low
+// half; 0 for a lane beyond the segment (a zero mask: never gathered).
+__device__ __forceinline__ unsigned composite(const uint16_t* perm_s, const uint16_t* sec_s, int col, bool valid) {
+    unsigned pk = 0;
+    if (valid) {
+        const unsigned c = perm_s[col];
+        pk = (c << 16) | (unsigned)sec_s[c];
+    }
+    return pk;
+}
+
+// Appends the live members (non-zero sector mask) of one chunk of 32 to the list, in member order.
+__device__ __forceinline__ int append_live(unsigned* list, int count, unsigned pk, int lane) {
+    const bool live = (pk & 0xffffu) != 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, live);
+    if (live) list[count + __popc(bal & ((1u << lane) - 1u))] = pk;
+    return count + __popc(bal);
+}
+
+// Pads the list to a multiple of eight with zero words and makes it visible to the warp.
+__device__ __forceinline__ void close_list(unsigned* list, int count, int lane) {
+    if (lane < 8) list[count + lane] = 0;
+    __syncwarp();
+}
+
+// Sequential sums over a compacted list (member order), eight entries per gather round.
+__device__ __forceinline__ void sum_list(double& acc0, double& acc1, const unsigned* list, int count, unsigned lanebit,
+                                         const double* base) {
+    for (int g = 0; g < count; g += 8) {
+        const uint4 wa = *(const uint4*)(list + g), wb = *(const uint4*)(list + g + 4);     // broadcast loads
+        group8(acc0, acc1, wa, wb, lanebit, base);
+    }
+    __syncwarp();
+}
+
+template <int NW>
+__global__ void __launch_bounds__(NW * 32, 1) conn_perm64_kernel(Tile64Args a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint16_t* s_perm = (uint16_t*)smem_raw;                       // [2][Sp]
+    uint16_t* s_sec = s_perm + 2 * (size_t)a.Sp;                  // [Sp]
+    double2* s_tab = (double2*)(s_sec + a.Sp);                    // [128]
+    double* s_tot = (double*)(s_tab + 128);                       // [NW][64]
+    double* s_part = s_tot + NW * kT;                             // [NW][64]
+    unsigned* s_list = (unsigned*)(s_part + NW * kT);             // [NW][2][kList] compacted composite words
+    __shared__ long long s_claim[2];
+    const int lane = threadIdx.x & 31;
+    const int w = threadIdx.x >> 5;
+    const unsigned lanebit = 1u << (lane >> 1);
+    float* pm = a.pm + (size_t)blockIdx.x * a.V * kT;
+    const double cor = (double)a.V / (double)(a.V - 1);           // ref:989
+    const int chunks16 = a.Sp >> 3;                               // 16-byte pieces of a row
+    for (int i = threadIdx.x; i < 128; i += NW * 32) s_tab[i] = g_logtab[i];
+    if (threadIdx.x == 0) {
+        s_claim[0] = (long long)atomicAdd(a.counter, 1ull);
+        s_claim[1] = (long long)atomicAdd(a.counter, 1ull);
+    }
+    __syncthreads();
+    long long item = s_claim[0], next_item = s_claim[1];
+    int buf = 0, cur_tile = -1;
+    if (item < a.items) {                                          // first permutation row of this CTA
+        const uint16_t* src = a.perm16 + (size_t)((int)(item % a.nchunks) * kChunk) * a.Sp;
+        for (int i = threadIdx.x; i < chunks16; i += NW * 32) cp_async_16(s_perm + 8 * i, src + 8 * i);
+    }
+    for (; item < a.items; item = next_item, next_item = s_claim[0]) {
+        __syncthreads();                                           // s_claim[0] read, previous item finished
+        if (threadIdx.x == 0) s_claim[0] = (long long)atomicAdd(a.counter, 1ull);
+        const int tileIdx = (int)(item / a.nchunks);
+        const int chunk = (int)(item % a.nchunks);
+        if (tileIdx != cur_tile) {                                 // sector masks of the new tile
+            const uint16_t* src = a.sec + (size_t)tileIdx * a.Sp;
+            for (int i = threadIdx.x; i < chunks16; i += NW * 32) cp_async_16(s_sec + 8 * i, src + 8 * i);
+            cur_tile = tileIdx;
+        }
+        const double* base = a.ET + (size_t)tileIdx * a.S * kPitch + 2 * lane;
+        const int g0 = a.gmap[tileIdx * kT + 2 * lane], g1 = a.gmap[tileIdx * kT + 2 * lane + 1];
+        const double obs0 = g0 >= 0 ? a.observed[g0] : 0.0, obs1 = g1 >= 0 ? a.observed[g1] : 0.0;
+        int ex0 = 0, ex1 = 0, ti0 = 0, ti1 = 0;
+        const int r_end = min(a.n, (chunk + 1) * kChunk);
+        for (int r = chunk * kChunk; r < r_end; ++r) {
+            cp_async_wait_all();                                   // this thread's pieces of the current row (and masks)
+            __syncthreads();                                       // ... and everybody else's
+            int rn = r + 1;                                        // the row this CTA processes next, if any
+            if (rn >= r_end) rn = (next_item < a.items) ? (int)(next_item % a.nchunks) * kChunk : -1;
+            if (rn >= 0) {
+                const uint16_t* src = a.perm16 + (size_t)rn * a.Sp;
+                uint16_t* dst = s_perm + (size_t)(buf ^ 1) * a.Sp;
+                for (int i = threadIdx.x; i < chunks16; i += NW * 32) cp_async_16(dst + 8 * i, src + 8 * i);
+            }
+            const uint16_t* perm_r = s_perm + (size_t)buf * a.Sp;
+            buf ^= 1;
+            // ---- node values (ref:978-987) ----
+            // The list of node k+NW is built while node k is summed: its member columns are fetched
+            // before the sums and turned into composite words after them.
+            double tot0 = 0.0, tot1 = 0.0;
+            unsigned* lst = s_list + (size_t)w * 2 * kList;
+            int cur = 0;
+            int k = w, beg = 0, end = 0, count = 0;
+            if (k < a.V) {
+                beg = __ldg(a.node_off + k);
+                end = __ldg(a.node_off + k + 1);
+                const int n0 = min(kSeg, end - beg);
+                const int c0 = lane < n0 ? __ldg(a.node_cols + beg + lane) : 0;
+                const int c1 = lane + 32 < n0 ? __ldg(a.node_cols + beg + 32 + lane) : 0;
+                count = append_live(lst, 0, composite(perm_r, s_sec, c0, lane < n0), lane);
+                if (n0 > 32) count = append_live(lst, count, composite(perm_r, s_sec, c1, lane + 32 < n0), lane);
+                close_list(lst, count, lane);
+            }
+            while (k < a.V) {
+                const int len = end - beg;
+                const int kn = k + NW;
+                int begn = 0, endn = 0, nn = 0, cn0 = 0, cn1 = 0;
+                if (kn < a.V) {                                    // next node's member columns, in flight under the sums
+                    begn = __ldg(a.node_off + kn);
+                    endn = __ldg(a.node_off + kn + 1);
+                    nn = min(kSeg, endn - begn);
+                    if (lane < nn) cn0 = __ldg(a.node_cols + begn + lane);
+                    if (lane + 32 < nn) cn1 = __ldg(a.node_cols + begn + 32 + lane);
+                }
+                double acc0 = 0.0, acc1 = 0.0;
+                sum_list(acc0, acc1, lst + cur * kList, count, lanebit, base);
+                for (int sb = beg + kSeg; sb < end; sb += kSeg) {  // nodes above 64 members: further segments, in order
+                    unsigned* l2 = lst + cur * kList;
+                    const int ns = min(kSeg, end - sb);
+                    const int c0 = lane < ns ? __ldg(a.node_cols + sb + lane) : 0;
+                    const int c1 = lane + 32 < ns ? __ldg(a.node_cols + sb + 32 + lane) : 0;
+                    int cnt = append_live(l2, 0, composite(perm_r, s_sec, c0, lane < ns), lane);
+                    if (ns > 32) cnt = append_live(l2, cnt, composite(perm_r, s_sec, c1, lane + 32 < ns), lane);
+                    close_list(l2, cnt, lane);
+                    sum_list(acc0, acc1, l2, cnt, lanebit, base);
+                }
+                const double q = (double)len, iq = __ldg(a.inv_q + k);
+                float2 pv;
+                if (a.log2_mode) {                                 // ref:982-983, float32 store of ref:972
+                    pv.x = pm_fast(acc0, q, iq, s_tab);
+                    pv.y = pm_fast(acc1, q, iq, s_tab);
+                } else {                                           // ref:986
+                    pv.x = (float)div_rn(acc0, q, iq);
+                    pv.y = (float)div_rn(acc1, q, iq);
+                }
+                __stcg((float2*)(pm + (size_t)k * kT) + lane, pv);
+                tot0 += (double)pv.x;                              // ref:984
+                tot1 += (double)pv.y;
+                if (kn < a.V) {
+                    unsigned* l2 = lst + (cur ^ 1) * kList;
+                    count = append_live(l2, 0, composite(perm_r, s_sec, cn0, lane < nn), lane);
+                    if (nn > 32) count = append_live(l2, count, composite(perm_r, s_sec, cn1, lane + 32 < nn), lane);
+                    close_list(l2, count, lane);
+                }
+                cur ^= 1;
+                k = kn; beg = begn; end = endn;
+            }
+            s_tot[w * kT + 2 * lane] = tot0;
+            s_tot[w * kT + 2 * lane + 1] = tot1;
+            __syncthreads();
+            // ---- p'Ap on the un-normalised values; the 1/tot^2 is applied once (ref:988-989) ----
+            double part0 = 0.0, part1 = 0.0;
+            for (int kk = w; kk < a.V; kk += NW) {
+                const int eb = __ldg(a.adj_off + kk), ee = __ldg(a.adj_off + kk + 1);
+                double s0 = 0.0, s1 = 0.0;
+                for (int e = eb; e < ee; ++e) {
+                    const int l = __ldg(a.adj_idx + e);
+                    const double wt = __ldg(a.adj_w + e);
+                    const float2 v = __ldcg((const float2*)(pm + (size_t)l * kT) + lane);
+                    s0 += wt * (double)v.x;
+                    s1 += wt * (double)v.y;
+                }
+                const float2 vk = __ldcg((const float2*)(pm + (size_t)kk * kT) + lane);
+                part0 += (double)vk.x * s0;
+                part1 += (double)vk.y * s1;
+            }
+            s_part[w * kT + 2 * lane] = part0;
+            s_part[w * kT + 2 * lane + 1] = part1;
+            __syncthreads();
+            if (w == 0) {
+                double t0 = 0.0, t1 = 0.0, p0 = 0.0, p1 = 0.0;
+#pragma unroll 8
+                for (int i = 0; i < NW; ++i) {
+                    t0 += s_tot[i * kT + 2 * lane];
+                    t1 += s_tot[i * kT + 2 * lane + 1];
+                    p0 += s_part[i * kT + 2 * lane];
+                    p1 += s_part[i * kT + 2 * lane + 1];
+                }
+                const double c0 = cor * (p0 / (t0 * t0)), c1 = cor * (p1 / (t1 * t1));
+                if (g0 >= 0) {
+                    if (c0 > obs0) ++ex0;                          // ref:990, strict
+                    if (fabs(c0 - obs0) <= a.tie_rel * fabs(obs0)) ++ti0;
+                    if (a.scores) a.scores[(size_t)g0 * a.n + r] = c0;
+                }
+                if (g1 >= 0) {
+                    if (c1 > obs1) ++ex1;
+                    if (fabs(c1 - obs1) <= a.tie_rel * fabs(obs1)) ++ti1;
+                    if (a.scores) a.scores[(size_t)g1 * a.n + r] = c1;
+                }
+            }
+            __syncthreads();
+        }
+        if (w == 0) {
+            if (g0 >= 0) {
+                if (ex0) atomicAdd(a.exceed + g0, ex0);
+                if (a.ties && ti0) atomicAdd(a.ties + g0, ti0);
+            }
+            if (g1 >= 0) {
+                if (ex1) atomicAdd(a.exceed + g1, ex1);
+                if (a.ties && ti1) atomicAdd(a.ties + g1, ti1);
+            }
+        }
+    }
+}
+
+// ET[tile][s][slot] = f(Y[gmap[tile*64+slot]][samples[s]]), f(x) = 2^x - 1 (log2 mode) or x; padding
+// slots are zeros.  sec[tile][s]: bit q set iff one of the slots 4q..4q+3 holds anything but a zero.
+__global__ void __launch_bounds__(256) et_prep64_kernel(const double* __restrict__ Y, int64_t ldy, int S, int Sp,
+                                                        const int32_t* __restrict__ samples,
+                                                        const int32_t* __restrict__ gmap, int log2_mode,
+                                                        double* __restrict__ ET, uint16_t* __restrict__ sec) {
+    __shared__ double tile[kT][33];
+    const int tileIdx = blockIdx.y;
+    const int s0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;        // 32 x 8
+    const int s = s0 + tx;
+    int col = 0;
+    if (s < S) col = samples ? samples[s] : s;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const int gl = ty + 8 * r;
+        const int g = gmap[tileIdx * kT + gl];
+        double v = 0.0;
+        if (g >= 0 && s < S) {
+            const double x = Y[(int64_t)g * ldy + col];
+            v = log2_mode ? (exp2(x) - 1.0) : x;
+        }
+        tile[gl][tx] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int sl = ty + 8 * r;
+        const double v0 = tile[tx][sl], v1 = tile[tx + 32][sl];
+        const unsigned b0 = __ballot_sync(0xffffffffu, !(v0 == 0.0)), b1 = __ballot_sync(0xffffffffu, !(v1 == 0.0));
+        if (s0 + sl < S) {
+            double* row = ET + ((int64_t)tileIdx * S + s0 + sl) * kPitch;
+            row[tx] = v0;
+            row[tx + 32] = v1;
+            if (tx == 0) {
+                unsigned m = 0;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    if ((b0 >> (4 * q)) & 0xfu) m |= 1u << q;
+                    if ((b1 >> (4 * q)) & 0xfu) m |= 1u << (8 + q);
+                }
+                sec[(int64_t)tileIdx * Sp + s0 + sl] = (uint16_t)m;
+            }
+        }
+    }
+}
+
+__global__ void perm16_kernel(const int32_t* __restrict__ perm, int n, int S, int Sp, uint16_t* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)n * Sp) return;
+    const int r = (int)(i / Sp), j = (int)(i % Sp);
+    out[i] = j < S ? (uint16_t)perm[(int64_t)r * S + j] : (uint16_t)0;
+}
+
+__global__ void identity_gmap_kernel(int32_t* gmap, const int32_t* __restrict__ order, int G, int slots) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < slots) gmap[i] = i < G ? (order ? order[i] : i) : -1;
+}
+
+__global__ void inv_size64_kernel(const int32_t* __restrict__ off, int V, double* __restrict__ inv_q) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < V) inv_q[k] = 1.0 / (double)(off[k + 1] - off[k]);
+}
+
+// pm_fast against the full-accuracy path on pseudo-random sums and node sizes.
+__global__ void selftest_pm_fast_kernel(int64_t n, uint64_t seed, unsigned long long* out) {
+    __shared__ double2 tab[128];
+    for (int i = threadIdx.x; i < 128; i += blockDim.x) tab[i] = g_logtab[i];
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t x = seed + 0x9E3779B97F4A7C15ull * (uint64_t)(i + 1);
+    x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 27; x *= 0x94D049BB133111EBull; x ^= x >> 31;
+    const uint64_t mant = x & 0xFFFFFFFFFFFFFull;
+    const int ex = (int)((x >> 52) % 64) - 20;                    // sums 2^-20 .. 2^43
+    double acc = __longlong_as_double((long long)(((uint64_t)(1023 + ex) << 52) | mant));
+    if ((x >> 59) == 0) acc = 0.0;
+    const int qi = (int)((x >> 40) % 4096) + 1;
+    const double q = (double)qi, iq = 1.0 / q;
+    const float f = pm_fast(acc, q, iq, tab), s = pm_log2_value(div_rn(acc, q, iq));
+    if (__float_as_uint(f) != __float_as_uint(s)) atomicAdd(out, 1ull);
+    // share of evaluations that left the fast path (reported, not an error)
+    const double t = acc * iq, y = log1p(t) * (1.0 / 0.693147);
+    const unsigned lo = (unsigned)__double2loint(y) & 0x1fffffffu;
+    if (!((lo - 0x10000000u + kGuard) >= 2u * kGuard && t >= 0.00390625 && t <= 1e30)) atomicAdd(out + 1, 1ull);
+}
+
+int ensure_logtab(sctda_ctx* ctx) {
+    if (ctx->attr_done & 0x100u) return SCTDA_OK;
+    double2 h[128];
+    for (int j = 0; j < 128; ++j) {
+        const long double c = 1.0L + ((long double)j + 0.5L) / 128.0L;
+        const double invc = (double)(1.0L / c);
+        h[j].x = invc;
+        h[j].y = (double)(-logl((long double)invc));
+    }
+    SCTDA_CUDA(ctx, cudaMemcpyToSymbol(g_logtab, h, sizeof(h)));
+    ctx->attr_done |= 0x100u;
+    return SCTDA_OK;
+}
+
+template <int NW>
+int launch64(sctda_ctx* ctx, const Tile64Args& a, int grid, size_t smem, cudaStream_t st) {
+    auto kern = conn_perm64_kernel<NW>;
+    SCTDA_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, NW * 32, smem, st>>>(a);
+    return SCTDA_OK;
+}
+
+}  // namespace
+
+// Shared-memory bytes the 64-gene kernel needs for S cells with NW warps.
+static size_t tile64_smem(int Sp, int NW) {
+    return (size_t)3 * Sp * 2 + 128 * sizeof(double2) + (size_t)2 * NW * kT * sizeof(double) + (size_t)NW * 2 * kList * sizeof(unsigned);
+}
+
+static int tile64_warps() {
+    static int nw = 0;
+    if (!nw) {
+        const char* e = getenv("SCTDA_CONN64_WARPS");
+        nw = e ? atoi(e) : 32;          // 32: node k -> warp k mod 32, the partial sums of conn.cu's kernel (same bits)
+        if (nw != 16 && nw != 24 && nw != 32) nw = 32;
+    }
+    return nw;
+}
+
+// True when sctda_conn_perm_test's shared-permutation call can run on the 64-gene kernel.
+bool sctda_tile64_eligible(const sctda_graph* gr) {
+    const int Sp = (gr->S + 7) & ~7;
+    return gr->S <= 65535 && tile64_smem(Sp, tile64_warps()) <= (size_t)220 * 1024;
+}
+
+// The shared-permutation test on 64-gene tiles.  d_order [G] (or NULL): gene of each tile slot.
+int sctda_conn_perm_tile64(sctda_ctx* ctx, const sctda_graph* gr, int G, const double* d_Y, int64_t ldy, int log2_mode,
+                           int n, const int32_t* d_perm, const int32_t* d_order, const double* d_observed,
+                           double tie_rel, int32_t* d_exceed, int32_t* d_ties, double* d_scores, cudaStream_t st) {
+    int rc = ensure_logtab(ctx);
+    if (rc) return rc;
+    const int tiles = (G + kT - 1) / kT;
+    const int Sp = (gr->S + 7) & ~7;
+    // workspace: ET | sec | gmap in WS_ET, perm16 in WS_MISC2, inv_q + queue head in WS_MISC
+    const size_t et_bytes = (size_t)tiles * gr->S * kPitch * sizeof(double);
+    const size_t sec_bytes = ((size_t)tiles * Sp * sizeof(uint16_t) + 255) & ~(size_t)255;
+    const size_t gmap_bytes = (size_t)tiles * kT * sizeof(int32_t);
+    unsigned char* ws = (unsigned char*)sctda_ws(ctx, WS_ET, et_bytes + sec_bytes + gmap_bytes);
+    if (!ws) return SCTDA_ERR_NOMEM;
+    double* ET = (double*)ws;
+    uint16_t* sec = (uint16_t*)(ws + et_bytes);
+    int32_t* gmap = (int32_t*)(ws + et_bytes + sec_bytes);
+    uint16_t* perm16 = (uint16_t*)sctda_ws(ctx, WS_MISC2, (size_t)n * Sp * sizeof(uint16_t));
+    if (!perm16) return SCTDA_ERR_NOMEM;
+    double* inv_q = (double*)sctda_ws(ctx, WS_MISC, (size_t)gr->V * sizeof(double) + 64);
+    if (!inv_q) return SCTDA_ERR_NOMEM;
+    unsigned long long* counter = (unsigned long long*)(inv_q + gr->V);
+    SCTDA_CUDA(ctx, cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
+    identity_gmap_kernel<<<(tiles * kT + 255) / 256, 256, 0, st>>>(gmap, d_order, G, tiles * kT);
+    SCTDA_LAUNCH_CHECK(ctx, "identity_gmap_kernel");
+    if (Sp != gr->S) SCTDA_CUDA(ctx, cudaMemsetAsync(sec, 0, (size_t)tiles * Sp * sizeof(uint16_t), st));
+    dim3 grid_p((gr->S + 31) / 32, tiles);
+    et_prep64_kernel<<<grid_p, 256, 0, st>>>(d_Y, ldy, gr->S, Sp, gr->d_samples, gmap, log2_mode, ET, sec);
+    SCTDA_LAUNCH_CHECK(ctx, "et_prep64_kernel");
+    perm16_kernel<<<(unsigned)cdiv64((int64_t)n * Sp, 256), 256, 0, st>>>(d_perm, n, gr->S, Sp, perm16);
+    SCTDA_LAUNCH_CHECK(ctx, "perm16_kernel");
+    inv_size64_kernel<<<(gr->V + 255) / 256, 256, 0, st>>>(gr->d_node_off, gr->V, inv_q);
+    SCTDA_LAUNCH_CHECK(ctx, "inv_size64_kernel");
+    Tile64Args a;
+    a.V = gr->V; a.S = gr->S; a.Sp = Sp; a.G = G; a.n = n; a.log2_mode = log2_mode;
+    a.nchunks = (n + kChunk - 1) / kChunk;
+    a.tiles = tiles;
+    a.items = (long long)tiles * a.nchunks;
+    a.node_off = gr->d_node_off; a.node_cols = gr->d_node_cols;
+    a.adj_off = gr->d_adj_off; a.adj_idx = gr->d_adj_idx; a.adj_w = gr->d_adj_w;
+    a.ET = ET; a.sec = sec; a.perm16 = perm16; a.gmap = gmap; a.inv_q = inv_q;
+    a.observed = d_observed; a.tie_rel = tie_rel > 0.0 ? tie_rel : 1e-9;
+    a.exceed = d_exceed; a.ties = d_ties; a.scores = d_scores; a.counter = counter;
+    long long grid64 = ctx->sm_count;                              // one CTA per SM
+    if (grid64 > a.items) grid64 = a.items;
+    const int grid = (int)grid64;
+    a.pm = (float*)sctda_ws(ctx, WS_PM, (size_t)grid * gr->V * kT * sizeof(float));
+    if (!a.pm) return SCTDA_ERR_NOMEM;
+    const int NW = tile64_warps();
+    const size_t smem = tile64_smem(Sp, NW);
+    SCTDA_TIME_BEGIN(ctx, st);
+    if (NW == 16) rc = launch64<16>(ctx, a, grid, smem, st);
+    else if (NW == 32) rc = launch64<32>(ctx, a, grid, smem, st);
+    else rc = launch64<24>(ctx, a, grid, smem, st);
+    SCTDA_TIME_END(ctx, st);
+    if (rc) return rc;
+    SCTDA_LAUNCH_CHECK(ctx, "conn_perm64_kernel");
+    return SCTDA_OK;
+}
+
+extern "C" int32_t sctda_selftest_pm_fast(sctda_ctx* ctx, int64_t n_trials, int64_t* out_mismatches,
+                                          int64_t* out_slow) {
+    if (!ctx || !out_mismatches || n_trials < 0) return SCTDA_ERR_INVALID;
+    SCTDA_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = ensure_logtab(ctx);
+    if (rc) return rc;
+    unsigned long long* d = (unsigned long long*)sctda_ws(ctx, WS_MISC, 256);
+    if (!d) return SCTDA_ERR_NOMEM;
+    SCTDA_CUDA(ctx, cudaMemset(d, 0, 2 * sizeof(unsigned long long)));
+    if (n_trials > 0) {
+        selftest_pm_fast_kernel<<<(unsigned)cdiv64(n_trials, 256), 256>>>(n_trials, 0x7113f457ull, d);
+        SCTDA_LAUNCH_CHECK(ctx, "selftest_pm_fast_kernel");
+    }
+    unsigned long long h[2] = {0, 0};
+    SCTDA_CUDA(ctx, cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost));
+    *out_mismatches = (int64_t)h[0];
+    if (out_slow) *out_slow = (int64_t)h[1];
+    return SCTDA_OK;
+}

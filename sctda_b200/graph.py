@@ -126,9 +126,11 @@ def node_stats(ctx, dg, Y, log2=True, dist=None, want_p=False):
     return out
 
 
-def conn_perm_test(ctx, dg, Y, perms, observed, log2=True, per_gene=False, want_scores=False, tie_rel=1e-9):
+def conn_perm_test(ctx, dg, Y, perms, observed, log2=True, per_gene=False, want_scores=False, tie_rel=1e-9,
+                   gene_order=None):
     """sctda_conn_perm_test.  Y [G, >=Ncells] float64 device; perms int32 device, [n, S]
-    (shared) or [G, n, S] (per_gene); observed [G] float64 device.
+    (shared) or [G, n, S] (per_gene); observed [G] float64 device; gene_order: int32 device
+    permutation of the genes (tile layout of the shared-permutation kernel, results unchanged).
     Returns (exceed int32 [G], ties int32 [G], scores float64 [G, n] or None) on the device."""
     import ctypes
     G = int(Y.shape[0])
@@ -146,10 +148,17 @@ def conn_perm_test(ctx, dg, Y, perms, observed, log2=True, per_gene=False, want_
     ties = torch.empty(G, dtype=torch.int32, device=dev)
     scores = torch.empty((G, n), dtype=torch.float64, device=dev) if want_scores else None
     p = _lib.ptr
-    rc = ctx.lib.sctda_conn_perm_test(ctx.handle, ctypes.byref(dg.struct), G, p(Y),
-                                      int(Y.stride(0)) if G else dg.Ncells, 1 if log2 else 0, n, p(perms), stride,
-                                      p(observed), float(tie_rel), p(exceed), p(ties), p(scores),
-                                      ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+    st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    if gene_order is not None and not per_gene:
+        assert gene_order.dtype == torch.int32 and gene_order.numel() == G and gene_order.is_contiguous()
+        rc = ctx.lib.sctda_conn_perm_test_ordered(ctx.handle, ctypes.byref(dg.struct), G, p(Y),
+                                                  int(Y.stride(0)) if G else dg.Ncells, 1 if log2 else 0, n, p(perms),
+                                                  p(gene_order), p(observed), float(tie_rel), p(exceed), p(ties),
+                                                  p(scores), st)
+    else:
+        rc = ctx.lib.sctda_conn_perm_test(ctx.handle, ctypes.byref(dg.struct), G, p(Y),
+                                          int(Y.stride(0)) if G else dg.Ncells, 1 if log2 else 0, n, p(perms), stride,
+                                          p(observed), float(tie_rel), p(exceed), p(ties), p(scores), st)
     ctx.check(rc)
     return exceed, ties, scores
 
