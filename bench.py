@@ -13,12 +13,18 @@ test over the rank's gene shard x all permutations.  The permutation block [n, S
 INPUT shared by all genes (SURVEY.md §7 H1 option i: 2e8 fresh per-gene permutations are
 16 TB of indices; the per-gene reference stream is exercised by the parity tests).
 
-JSON line: see the task contract.  `value` = device-resident throughput; `e2e` = the same
-through graph.conn_perm_test_host with pinned HOST buffers (H2D of table + permutations and
-D2H of the counts inside the timed region); `roofline` = the dominant kernel
-(conn_perm_kernel) against the measured HBM copy bandwidth with SURVEY.md §8d's
-algorithmic bytes (4*S + 8*S/n per gene·perm); `cpu_baseline` = the oracle port on a
-bounded sample of the same workload.
+JSON line: see the task contract.  `value` = device-resident throughput, the final gather of
+the per-gene counts of all ranks included; `e2e` = the same through graph.conn_perm_test_host
+with pinned HOST buffers (H2D of table + permutations, the tile layout and D2H of the counts
+inside the timed region); `roofline` = the dominant kernel (conn_perm64_kernel) against the
+measured HBM copy bandwidth with SURVEY.md §8d's algorithmic bytes (4*S + 8*S/n per
+gene·perm), its duration averaged over all timed steps; `cpu_baseline` = the oracle port on
+a bounded sample of the same workload.
+
+`mapper`: the Mapper build of BASELINE.json's metric, 100,000 cells x 2,000 genes (configs[2]) at
+EVERY N including 1 (cells/s; patches sharded over the ranks for N > 1), with the FP64
+contraction's roofline in both conventions (SURVEY 8d's algorithmic flops without symmetry
+credit, and the flops of the tiles actually executed); configs[1] (20k x 5k) rides along at N = 1.
 """
 import argparse
 import json
@@ -65,6 +71,7 @@ def workload_config(a, n_gpus):
                         % (a.nodes, a.genes, a.perms, a.cells, n_gpus),
             'nodes': a.nodes, 'cells': a.cells, 'genes': a.genes, 'perms': a.perms,
             'permutations': 'one shared [n,S] int32 block (input)', 'l2': 'inputs_exceed_l2',
+            'final_gather': 'counts of all ranks gathered on rank 0 inside the timed region',
             'parallelism': 'genes/%d' % n_gpus}
 
 
@@ -127,6 +134,17 @@ class ClockSampler(object):
 _W = {}
 
 
+def _one_blas_thread():
+    """One BLAS / OpenMP thread in this process: the reference is a per-gene loop that one process
+    per core runs gene-parallel; a multithreaded numpy.dot inside every worker oversubscribes the
+    cores (round 1: 4x slower at N = 1 than under torchrun, which exports OMP_NUM_THREADS=1)."""
+    try:
+        import threadpoolctl
+        _W['tp'] = threadpoolctl.threadpool_limits(limits=1)
+    except Exception:
+        pass
+
+
 def _cpu_init(members, adj_dense, Y, perms):
     from oracle import conn_oracle as co
     V = len(members)
@@ -141,31 +159,80 @@ def _cpu_gene(i):
         return float(co.connectivity_pvalue(st, 'g%d' % i, n=_W['perms'].shape[0], perms=_W['perms']))
 
 
-def cpu_sample(a, n_genes, n_perms, procs):
-    """Times the oracle on `n_genes` genes x `n_perms` permutations of the bench workload
-    with `procs` worker processes.  Returns (gene*perms/s, seconds)."""
-    import multiprocessing as mp
-    from sctda_b200 import synth
-    members, adj, _ = synth.connectivity_case(a.cells, a.nodes, 1, seed=synth.SEED)
-    Y = synth.expression_genes_numpy(n_genes, a.cells, seed=synth.SEED)
-    rng = numpy.random.RandomState(7)
-    perms = numpy.stack([rng.permutation(a.cells) for _ in range(n_perms)]).astype(numpy.int32)
-    dense = adj.toarray()
-    if procs <= 1:
-        _cpu_init(members, dense, Y, perms)
+class CpuArm(object):
+    """The oracle port (oracle/conn_oracle.py, the reference's per-gene loop ref:966-992) on the bench
+    graph with `procs` single-threaded worker processes; sample(n_genes) times n_genes genes x all
+    permutations of the block."""
+
+    def __init__(self, a, n_perms, procs, max_genes):
+        import multiprocessing as mp
+        from sctda_b200 import synth
+        members, adj, _ = synth.connectivity_case(a.cells, a.nodes, 1, seed=synth.SEED)
+        self.Y = synth.expression_genes_numpy(max_genes, a.cells, seed=synth.SEED)
+        rng = numpy.random.RandomState(7)
+        perms = numpy.stack([rng.permutation(a.cells) for _ in range(n_perms)]).astype(numpy.int32)
+        _one_blas_thread()
+        _cpu_init(members, adj.toarray(), self.Y, perms)               # inherited by the forked workers
+        self.n_perms, self.procs = n_perms, procs
+        self.pool = mp.get_context('fork').Pool(procs, initializer=_one_blas_thread) if procs > 1 else None
+        if self.pool:
+            self.pool.map(_cpu_gene, range(min(procs, max_genes)), chunksize=1)      # spin-up, untimed
+
+    def sample(self, n_genes, offset=0):
+        idx = [(offset + i) % self.Y.shape[0] for i in range(n_genes)]
         t0 = time.perf_counter()
-        for i in range(n_genes):
-            _cpu_gene(i)
+        if self.pool:
+            self.pool.map(_cpu_gene, idx, chunksize=1)
+        else:
+            for i in idx:
+                _cpu_gene(i)
         dt = time.perf_counter() - t0
-    else:
-        ctx = mp.get_context('fork')
-        _cpu_init(members, dense, Y, perms)            # inherited by the forked workers
-        with ctx.Pool(procs) as pool:
-            pool.map(_cpu_gene, range(min(procs, n_genes)))        # spin-up outside the timed region
-            t0 = time.perf_counter()
-            pool.map(_cpu_gene, range(n_genes), chunksize=1)
-            dt = time.perf_counter() - t0
-    return n_genes * n_perms / dt, dt
+        return n_genes * self.n_perms / dt, dt
+
+    def close(self):
+        if self.pool:
+            self.pool.close()
+            self.pool.join()
+
+
+def mapper_cpu_sample(budget_s=20.0, N=100000, G=2000, r=30, gain=3.0, metric='euclidean', max_patch=5000):
+    """The Mapper oracle (oracle/mapper_oracle.py) on a BOUNDED sample of the bench workload: the cover
+    of the 100k x 2k table is cut as the device path cuts it (PCA lens on the host), then patches
+    (those up to `max_patch` cells, in random order) are clustered one by one until `budget_s` is
+    spent.  The per-patch clustering is O(m^2 G); the build rate of the whole table is extrapolated
+    by the m^2 share of the sample: cells/s = N * (sum m^2 of the sample / sum m^2 of all patches) / seconds."""
+    from oracle import mapper_oracle as mo
+    from sctda_b200 import synth
+    t_all = time.perf_counter()
+    X = synth.expression_genes_numpy(G, N, seed=synth.SEED + 11).T.copy()
+    Xc = X - X.mean(axis=0)
+    w, v = numpy.linalg.eigh(Xc.T @ Xc)
+    lens = Xc @ v[:, [-1, -2]]
+    del Xc
+    Xn, _ = mo.row_normalize(X, metric)
+    bins, _ = mo.cover(lens, r, gain, True)
+    sizes = numpy.array([c.size for c in bins], dtype=numpy.float64)
+    rng = numpy.random.RandomState(3)
+    done_m2, n_done, t_spent = 0.0, 0, 0.0
+    for b in rng.permutation(len(bins)):
+        cells = bins[int(b)]
+        if cells.size < 2 or cells.size > max_patch:
+            continue
+        t0 = time.perf_counter()
+        mo.cluster_bin(mo.gram(Xn, cells, cells), max_K=5)
+        t_spent += time.perf_counter() - t0
+        done_m2 += float(cells.size) ** 2
+        n_done += 1
+        if t_spent > budget_s:
+            break
+    total_m2 = float((sizes ** 2).sum())
+    est = N * (done_m2 / total_m2) / t_spent
+    return {'value': est, 'unit': 'cells/s', 'cores': os.cpu_count(), 'kind': 'port',
+            'workload': 'Mapper build: %d cells x %d genes, %s metric, PCA lens, resolution %d, gain %g, max_K 5' % (N, G, metric, r, gain),
+            'sample': '%d of %d patches of that cover (patches up to %d cells, random order; %.3g of sum m^2) clustered by '
+                      'oracle/mapper_oracle.py in %.1f s (Gram matrices by an OpenMP fma loop, MST / selection single-threaded '
+                      'numpy); whole-build rate extrapolated by the m^2 share; setup (table, lens, cover) %.0f s untimed'
+                      % (n_done, len(bins), max_patch, done_m2 / total_m2, t_spent, time.perf_counter() - t_all - t_spent)}
 
 
 def run_reference(a):
@@ -173,25 +240,34 @@ def run_reference(a):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    n_perms = 200
-    n_genes = 2 * cores
-    for _ in range(a.warmup):
-        cpu_sample(a, min(cores, 4), 20, min(cores, 4))
-    vals, times = [], []
-    for _ in range(a.steps):
-        v, dt = cpu_sample(a, n_genes, n_perms, cores)
-        vals.append(v)
+    n_perms = 2000                                     # >= 2,000 permutations per gene: get_gene's Python loops are
+    n_genes = cores                                    # amortised as in the real workload (10,000), one gene per core and step
+    arm = CpuArm(a, n_perms, cores, max(cores, 8) * 4)
+    for i in range(max(0, min(a.warmup, 1))):          # one warm-up step is enough for a CPU loop (the pool is already spun up)
+        arm.sample(n_genes, offset=i * n_genes)
+    times = []
+    for i in range(a.steps):
+        v, dt = arm.sample(n_genes, offset=(i + 1) * n_genes)
         times.append(dt)
+    arm.close()
     total = n_genes * n_perms * a.steps / sum(times)
-    sample = ('%d genes x %d permutations of the same graph per step, one process per core, '
-              'oracle/conn_oracle.py (numpy restatement of ref:966-992)' % (n_genes, n_perms))
+    sample = ('%d genes x %d permutations of the same graph per step, one single-threaded process per core '
+              '(threadpoolctl: 1 BLAS thread each), oracle/conn_oracle.py (numpy restatement of ref:966-992)'
+              % (n_genes, n_perms))
+    mapper_leg = None
+    if not a.no_mapper:
+        try:
+            mapper_leg = mapper_cpu_sample()
+        except Exception as e:                          # the conn line must not be lost to the secondary leg
+            mapper_leg = {'error': repr(e)}
     line = {'metric': METRIC, 'value': total, 'unit': UNIT, 'n_gpus': a.gpus, 'steps': a.steps, 'warmup': a.warmup,
             'ms_per_step': 1e3 * sum(times) / a.steps, 'higher_is_better': True, 'scaling': 'strong',
             'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'impl': 'reference',
             'config': workload_config(a, a.gpus),
-            'cpu_baseline': {'value': total, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
+            'cpu_baseline': {'value': total, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample,
+                             'blas_threads_per_worker': 1},
             'e2e': {'value': total, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
-            'gpu_launches': 0}
+            'gpu_launches': 0, 'mapper': mapper_leg}
     print(json.dumps(line))
 
 
@@ -217,19 +293,22 @@ def fp64_probe_tflops(dev):
     return best
 
 
-def run_mapper(a, ctx, dev, steps, warmup, rank=0, world=1):
-    """world == 1: BASELINE.json configs[1] (20k x 5k, correlation, r=30, gain 3) on one GPU.
-    world > 1: configs[2] (100k cells x 2k genes, euclidean), per-patch clustering sharded over the
-    ranks by descending m^2, labels exchanged by one all_gather (NCCL), the rest replicated."""
+def executed_tile_flops(sizes, G, tile=128):
+    """Flops of the 128 x 128 output tiles gemm_kernel executes for symmetric patch Gram matrices: the upper
+    triangle of tiles only (T(T+1)/2 tiles of a patch of ceil(m/128) = T tile rows), every tile counted
+    in full (edge tiles compute their padding)."""
+    T = (numpy.asarray(sizes, dtype=numpy.int64) + tile - 1) // tile
+    return 2.0 * G * float(tile * tile) * float((T * (T + 1) // 2).sum())
+
+
+def mapper_build_record(a, ctx, dev, N, G, metric, r, gain, steps, warmup, rank, world, peak, with_e2e):
+    """Times `steps` Mapper builds (normalise -> cover -> per-patch clustering -> nodes -> nerve, inputs
+    resident; patches sharded over the ranks when world > 1) and returns the record."""
     import torch
     import torch.distributed as dist
     from sctda_b200 import mapper, synth
-    if world > 1:
-        N, G, metric = 100000, 2000, 'euclidean'
-    else:
-        N, G, metric = a.mapper_cells, a.mapper_genes, a.mapper_metric
-    r, gain = a.mapper_resolution, a.mapper_gain
     X = synth.expression_genes_torch(G, N, seed=synth.SEED + 11, device=dev).T.contiguous()      # cells x genes
+    torch.cuda.synchronize()
     t0 = time.perf_counter()
     lens = mapper.pca_lens_device(X)
     if world > 1:
@@ -241,30 +320,34 @@ def run_mapper(a, ctx, dev, steps, warmup, rank=0, world=1):
         if world > 1:
             return mapper.build_graph_distributed(ctx, X, lens, r, gain, metric=metric, profile=prof)
         return mapper.build_graph_device(ctx, X, lens, r, gain, metric=metric, profile=prof)
-    prof = {}
+
+    def timed(n):
+        times, gemm, prof, res = [], [], {}, None
+        for _ in range(n):
+            prof = {}
+            if world > 1:
+                dist.barrier()
+            res = build(prof)
+            t = torch.tensor([prof['total_ms']], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            times.append(float(t.item()))
+            gemm.append(prof['gemm_ms'])
+        return times, gemm, prof, res
     for _ in range(max(1, warmup)):
-        build(prof)
-    times, gemm = [], []
-    for _ in range(steps):
-        prof = {}
-        if world > 1:
-            dist.barrier()
-        res = build(prof)
-        t = torch.tensor([prof['total_ms']], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        times.append(float(t.item()))
-        gemm.append(prof['gemm_ms'])
+        build({})
+    times, gemm, prof, res = timed(steps)
     bin_off = res.bin_off.cpu().numpy().astype(numpy.int64)
     m = bin_off[1:] - bin_off[:-1]
     sum_m2 = float((m * m).sum())
     flops = 2.0 * G * sum_m2 / world                          # this rank's share (LPT balances m^2)
+    flops_exec = executed_tile_flops(m, G) / world
     # the build has one host synchronisation (patch sizes come back to plan the batches): on a busy
     # host single builds are delayed by tens of ms, so the figure is the MEDIAN build; every build is listed
     ms = float(numpy.median(times))
     gms = float(numpy.median(gemm))
-    peak = fp64_probe_tflops(dev)
-    out = {'metric': 'Mapper build cells/s', 'value': N / (ms * 1e-3), 'unit': 'cells/s', 'ms_per_build': ms, 'ms_builds': [round(x, 2) for x in times], 'ms_per_build_mean': float(numpy.mean(times)), 'n_gpus': world,
+    out = {'metric': 'Mapper build cells/s', 'value': N / (ms * 1e-3), 'unit': 'cells/s', 'ms_per_build': ms,
+           'ms_builds': [round(x, 2) for x in times], 'ms_per_build_mean': float(numpy.mean(times)), 'n_gpus': world,
            'config': {'workload': 'Mapper build: %d cells x %d genes, %s metric, PCA lens, resolution %d, gain %g, '
                                   'max_K 5, %d B200%s' % (N, G, metric, r, gain, world,
                                                           ', patches sharded by descending m^2' if world > 1 else ''),
@@ -274,28 +357,22 @@ def run_mapper(a, ctx, dev, steps, warmup, rank=0, world=1):
                          if k.endswith('_ms') and k not in ('total_ms', 'gemm_ms', 'host_ms') and isinstance(v, (int, float))},
            'pca_lens_ms_untimed': lens_ms, 'host_ms': prof.get('host_ms'),
            'roofline': {'bound': 'tensor', 'achieved': flops / (gms * 1e-3) / 1e12, 'peak': peak, 'unit': 'TFLOP/s',
-                        'frac': flops / (gms * 1e-3) / 1e12 / peak, 'traffic': None, 'kernel': 'gemm_kernel (FP64 DMMA)',
-                        'kernel_ms': gms, 'flops': flops,
-                        'executed_flops': 'upper-triangular 128x128 tiles only (the Gram tile is symmetric bit for bit): '
-                                          'about half of `flops`, which is SURVEY.md 8d\'s algorithmic 2*G*sum m_b^2 '
-                                          'without symmetry credit, so frac can exceed 1',
+                        'frac': flops / (gms * 1e-3) / 1e12 / peak,
+                        'achieved_executed': flops_exec / (gms * 1e-3) / 1e12,
+                        'frac_executed': flops_exec / (gms * 1e-3) / 1e12 / peak,
+                        'traffic': None, 'kernel': 'gemm_kernel (FP64 DMMA)', 'kernel_ms': gms, 'flops': flops,
+                        'flops_executed': flops_exec,
+                        'conventions': '`frac`: SURVEY.md 8d\'s algorithmic 2*G*sum m_b^2, no symmetry credit (can exceed 1); '
+                                       '`frac_executed`: the 128x128 tiles the kernel runs (upper triangle of every '
+                                       'patch Gram tile, mirrored on the way out) -- the fraction of the tensor pipe '
+                                       'actually used',
                         'peak_source': 'torch.matmul float64 6144^3 (cuBLAS DGEMM) probe in this run'}}
     # the opt-in split-precision contraction (sctda_set_precision(ctx, 1): tcgen05 kind::f16 on (hi, lo)
     # half-precision operand pairs, distances within 1e-5) on the same build; the headline above stays
     # the FP64 build whose graph is identical to the oracle's
     with ctx.precision('fp16x3'):
         build({})
-        t2, g2 = [], []
-        for _ in range(steps):
-            prof2 = {}
-            if world > 1:
-                dist.barrier()
-            res2 = build(prof2)
-            t = torch.tensor([prof2['total_ms']], dtype=torch.float64, device=dev)
-            if world > 1:
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            t2.append(float(t.item()))
-            g2.append(prof2['gemm_ms'])
+        t2, g2, prof2, res2 = timed(max(2, steps // 2))
     ms2, gms2 = float(numpy.median(t2)), float(numpy.median(g2))
     same = bool(res2.V == res.V and res2.E == res.E and res2.node_members.shape == res.node_members.shape and
                 (res2.node_members == res.node_members).all().item() and (res2.edges == res.edges).all().item())
@@ -309,7 +386,7 @@ def run_mapper(a, ctx, dev, steps, warmup, rank=0, world=1):
                             'graph_identical_to_fp64_build': same, 'nodes': int(res2.V), 'edges': int(res2.E)}
     # end to end through the reference-facing call: host table and host lens in, networkx graph,
     # node lists and patches out (H2D of the table, D2H of the CSR / edges, graph object built on the host)
-    if world == 1:
+    if with_e2e and world == 1:
         Xh = X.cpu().numpy()
         lens_h = lens.cpu().numpy()
         mapper.mapper_graph(Xh[:2000], lens_h[:2000], r, gain, metric=metric, verbose=False)       # warm-up
@@ -320,25 +397,24 @@ def run_mapper(a, ctx, dev, steps, warmup, rank=0, world=1):
                       'd2h_bytes': int(4 * (2 * prof['Mtot'] + 2 * prof['E'] + prof['V'] + r * r + 2)),
                       'api': 'sctda_b200.mapper.mapper_graph(host table, host lens) -> (networkx.Graph, all_clusters, patches)'}
         assert Gx.number_of_nodes() == prof['V'] and Gx.number_of_edges() == prof['E']
+        del Xh
     del X
     torch.cuda.empty_cache()
     return out
 
 
-def mapper_cpu_sample():
-    """The Mapper oracle on BASELINE.json configs[0] scale (1,000 cells x 2,000 genes, r=20, gain 2)."""
-    from oracle import mapper_oracle as mo
-    from sctda_b200 import synth
-    X = synth.expression_genes_numpy(2000, 1000, seed=synth.SEED + 11).T.copy()
-    Xc = X - X.mean(axis=0)
-    u, s_, _ = numpy.linalg.svd(Xc, full_matrices=False)
-    lens = u[:, :2] * s_[:2]
-    t0 = time.perf_counter()
-    edges, clusters, _ = mo.mapper_graph(X, lens, 20, 2.0, metric='correlation')
-    dt = time.perf_counter() - t0
-    return {'value': 1000 / dt, 'unit': 'cells/s', 'cores': os.cpu_count(), 'kind': 'port',
-            'sample': 'oracle/mapper_oracle.py on 1,000 cells x 2,000 genes, r=20, gain 2 (%d nodes, %d edges), %.1f s; '
-                      'Gram matrices by an OpenMP fma loop, the rest single-threaded numpy' % (len(clusters), len(edges), dt)}
+def run_mapper(a, ctx, dev, steps, warmup, rank=0, world=1):
+    """BASELINE.json's Mapper metric: configs[2], 100,000 cells x 2,000 genes (euclidean, r=30, gain 3), at
+    every N: one GPU builds it alone, N > 1 shard the per-patch clustering by descending m^2 (labels
+    exchanged by one all_gather, the rest replicated).  At N = 1 configs[1] (20k x 5k, correlation) is
+    reported as `config2`."""
+    peak = fp64_probe_tflops(dev)
+    r, gain = a.mapper_resolution, a.mapper_gain
+    out = mapper_build_record(a, ctx, dev, 100000, 2000, 'euclidean', r, gain, steps, warmup, rank, world, peak, True)
+    if world == 1:
+        out['config2'] = mapper_build_record(a, ctx, dev, a.mapper_cells, a.mapper_genes, a.mapper_metric, r, gain,
+                                             max(2, steps // 2), 1, rank, world, peak, False)
+    return out
 
 
 # ---------------------------------------------------------------------------------------------
@@ -361,15 +437,24 @@ def run_own(a):
     ctx.set_kernel_timing(True)
 
     # ---- inputs, resident in HBM before the timed region ----
+    from sctda_b200 import geneorder
     members, adj, _ = synth.connectivity_case(a.cells, a.nodes, 1, seed=synth.SEED)
     dg = graph.DeviceGraph(members, adj, numpy.arange(a.cells), a.cells, local)
     g_lo = (a.genes * rank) // world
     g_hi = (a.genes * (rank + 1)) // world
     G = g_hi - g_lo
+    Gmax = -(-a.genes // world)                                   # the largest shard (gather buffers are padded to it)
     Y = synth.expression_genes_torch(G, a.cells, seed=synth.SEED, device=dev, gene_offset=g_lo)
     perms = synth.permutation_block_torch(a.perms, a.cells, seed=synth.SEED + 2, device=dev)
     observed = graph.node_stats(ctx, dg, Y, log2=True)['conn']
     torch.cuda.synchronize()
+    # the tile layout of the table (a plan, like the CSR of the graph: made once per table)
+    t0 = time.perf_counter()
+    order = geneorder.gene_order(Y)
+    torch.cuda.synchronize()
+    plan_ms = 1e3 * (time.perf_counter() - t0)
+    sector_density = geneorder.sector_density(Y[:4096], geneorder.gene_order(Y[:4096]))
+    sector_density_natural = geneorder.sector_density(Y[:4096])
 
     def barrier():
         torch.cuda.synchronize()
@@ -377,8 +462,21 @@ def run_own(a):
             dist.barrier()
         torch.cuda.synchronize()
 
+    gathered = [None]
+
     def step():
-        return graph.conn_perm_test(ctx, dg, Y, perms, observed, log2=True)
+        """One pass of the test over this rank's gene shard, then the final gather ("... to
+        exceed counts for all genes on device 0"): the only collective of the path."""
+        ex, ties, _ = graph.conn_perm_test(ctx, dg, Y, perms, observed, log2=True, gene_order=order)
+        if world > 1:
+            pad = torch.zeros(Gmax, dtype=torch.int32, device=dev)
+            pad[:G] = ex
+            buf = torch.empty(world * Gmax, dtype=torch.int32, device=dev) if rank == 0 else None
+            dist.gather(pad, list(buf.view(world, Gmax).unbind(0)) if rank == 0 else None, dst=0)
+            gathered[0] = buf
+        else:
+            gathered[0] = ex
+        return ex, ties
 
     for _ in range(a.warmup):
         step()
@@ -390,13 +488,12 @@ def run_own(a):
         barrier()
         e0.record()
         for _ in range(a.steps):
-            ex, ties, _ = step()
+            ex, ties = step()
+            kernel_ms.append(ctx.last_kernel_ms())                # waits for this step's kernel (events recorded by the library)
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
     launches = ctx.launch_count() - l0
-    # the dominant kernel alone (events recorded by the library around conn_perm_kernel, last timed step)
-    kernel_ms.append(ctx.last_kernel_ms())
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -414,12 +511,23 @@ def run_own(a):
         Oh = observed.cpu().pin_memory()
         del Y, perms
         torch.cuda.empty_cache()
-        graph.conn_perm_test_host(ctx, dg, Yh, Ph, Oh, log2=True)       # warm-up (allocations)
+
+        def e2e_step():
+            counts = graph.conn_perm_test_host(ctx, dg, Yh, Ph, Oh, log2=True)
+            if world > 1:                                          # the per-rank counts meet on rank 0 (host)
+                pad = torch.zeros(Gmax, dtype=torch.int32, device=dev)
+                pad[:G] = counts.to(dev)
+                buf = torch.empty(world * Gmax, dtype=torch.int32, device=dev) if rank == 0 else None
+                dist.gather(pad, list(buf.view(world, Gmax).unbind(0)) if rank == 0 else None, dst=0)
+                if rank == 0:
+                    counts = buf.cpu()
+            return counts
+        e2e_step()                                                 # warm-up (allocations)
         barrier()
-        e2e_steps = min(a.steps, 2)
+        e2e_steps = min(a.steps, 3)
         e0.record()
         for _ in range(e2e_steps):
-            counts = graph.conn_perm_test_host(ctx, dg, Yh, Ph, Oh, log2=True)
+            counts = e2e_step()
         e1.record()
         barrier()
         t2 = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -428,7 +536,9 @@ def run_own(a):
         assert int(counts.sum()) >= 0
         e2e = {'value': float(a.genes) * a.perms * e2e_steps / (float(t2.item()) * 1e-3), 'unit': UNIT, 'steps': e2e_steps,
                'h2d_bytes_per_step': int(Yh.numel() * 8 + Ph.numel() * 4 + Oh.numel() * 8),
-               'd2h_bytes_per_step': int(counts.numel() * 4), 'ms_per_step': float(t2.item()) / e2e_steps}
+               'd2h_bytes_per_step': int(G * 4), 'ms_per_step': float(t2.item()) / e2e_steps,
+               'includes': 'H2D of the table, the permutation block and the observed scores; the tile layout '
+                           '(gene order) of the uploaded table; the kernel; D2H of the counts; for N > 1 the gather on rank 0'}
 
     # ---- roofline of the dominant kernel ----
     peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
@@ -438,7 +548,7 @@ def run_own(a):
     else:
         peak, peak_src = 6650.0, 'B200_PROFILING.md fallback (of fallback)'
     bytes_per_unit = 4.0 * a.cells + 8.0 * a.cells / a.perms
-    k_ms = float(numpy.mean(kernel_ms))
+    k_ms = float(numpy.mean(kernel_ms))                          # mean over all timed steps
     achieved = bytes_per_unit * G * a.perms / (k_ms * 1e-3) / 1e9
     traffic = None                                               # DRAM bytes of this launch, from the committed ncu capture
     tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
@@ -450,12 +560,12 @@ def run_own(a):
     # on-chip view: with the permutation block shared, every gene*perm gathers 8*Mtot bytes of table
     # rows from L2 plus the float32 node values of the sparse product (model, matches ncu's
     # l1tex__m_xbar2l1tex_read_bytes to a few per cent); ceiling = measured L2 -> SM read bandwidth
-    l2_bytes_per_unit = 8.0 * dg.Mtot + 4.0 * dg.V + 4.0 * (dg.nnz + dg.V) + 4.0 * dg.Mtot / 32.0
+    l2_bytes_per_unit = 8.0 * dg.Mtot * sector_density + 4.0 * dg.V + 4.0 * (dg.nnz + dg.V) + 4.0 * dg.Mtot / 64.0
     l2_peak = ctx.probe_l2_read_gbs()
     l2_ach = l2_bytes_per_unit * G * a.perms / (k_ms * 1e-3) / 1e9
     roof = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
             'traffic': traffic, 'traffic_note': 'bytes per launch = ncu dram__bytes_read+write per gene*perm (profiles/traffic.json) x units of this launch; algorithmic bytes per launch = algorithmic_bytes_per_unit x units',
-            'kernel': 'conn_perm_kernel', 'kernel_ms': k_ms, 'peak_source': peak_src,
+            'kernel': 'conn_perm64_kernel', 'kernel_ms': k_ms, 'kernel_ms_steps': [round(x, 2) for x in kernel_ms], 'peak_source': peak_src,
             'algorithmic_bytes_per_unit': bytes_per_unit,
             'onchip': {'bound': 'l2', 'achieved': l2_ach, 'peak': l2_peak, 'unit': 'GB/s', 'frac': l2_ach / l2_peak,
                        'bytes_per_unit': l2_bytes_per_unit, 'peak_source': 'sctda_probe_l2_read_gbs in this run'},
@@ -475,14 +585,20 @@ def run_own(a):
     if rank == 0:
         cpu = None
         if world == 1 and not a.no_cpu:
-            v, dt = cpu_sample(a, 8, 400, 1)
-            cpu = {'value': v, 'unit': UNIT, 'cores': 1, 'kind': 'port',
-                   'sample': '8 genes x 400 permutations of the same graph, single process, %.1f s' % dt}
+            arm = CpuArm(a, 1000, 1, 8)
+            v, dt = arm.sample(4)
+            cpu = {'value': v, 'unit': UNIT, 'cores': 1, 'kind': 'port', 'blas_threads_per_worker': 1,
+                   'sample': '4 genes x 1,000 permutations of the same graph, one single-threaded process, %.1f s '
+                             '(oracle/conn_oracle.py)' % dt}
+        roof['sector_density'] = {'planned_order': sector_density, 'table_order': sector_density_natural,
+                                  'note': 'share of 32-byte sectors (4 genes x 1 cell) of the transposed table that hold a '
+                                          'non-zero, first 4,096 genes of this rank: the kernel requests only those'}
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': a.steps,
                 'warmup': a.warmup, 'ms_per_step': ms_max / a.steps, 'higher_is_better': True, 'scaling': 'strong',
                 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': workload_config(a, world),
                 'clocks': clocks.summary(), 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roof,
-                'cpu_baseline': cpu, 'tie_genes': int((ties > 0).sum().item()), 'mapper': mapper_line}
+                'cpu_baseline': cpu, 'plan_ms_untimed': plan_ms,
+                'tie_genes': int((ties > 0).sum().item()), 'mapper': mapper_line}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

@@ -23,6 +23,8 @@ Shim (everything that differs from running the file under Python 2):
                                          cannot write to the text-mode handles of ref:819-826)
   S7  pylab, matplotlib_venn, requests, sakmapper, mpl_toolkits.mplot3d -> inert stand-ins
   S8  numpy.infty                     -> numpy.inf               (textual; attribute removed in numpy 2)
+  S9  dict.values() inside numpy.array -> list(dict.values())    (textual, ref:1118 only; a Py2 dict.values()
+                                                                   is a list)
 
 Run:  python oracle/gen_golden.py          (rewrites tests/golden/)
 """
@@ -129,6 +131,9 @@ def load_reference():
         src = f.read()
     src = _py2_print_to_call(src)
     src = src.replace('numpy.infty', 'numpy.inf')                                # S8 (textual)
+    s9 = 'self.get_gene(genis)[0].values() for genis in lista'
+    assert src.count(s9) == 1
+    src = src.replace(s9, 'list(self.get_gene(genis)[0].values()) for genis in lista')      # S9 (textual)
     # import the real third-party modules first so that they never see the stand-ins below
     import pandas, scipy.cluster.hierarchy, scipy.interpolate, scipy.optimize, scipy.signal  # noqa: F401
     import scipy.spatial.distance, scipy.stats, sklearn.cluster, sklearn.metrics.pairwise  # noqa: F401
@@ -257,6 +262,17 @@ def run_case(ref, prefix, n_perm, seed, rooted):
             cen = c.centroid(gi)
             per_gene[str(gi)]['centroid'] = [None if v is None else float(v) for v in cen]
     out['per_gene'] = per_gene
+    # gene x gene matrices over the nodes (ref:1111-1190) on a few genes (the constant, the all-zero
+    # and the single-cell gene are left out: their profiles divide by zero in the reference)
+    lista = genes[3:11]
+    with numpy.errstate(invalid='ignore', divide='ignore'):
+        out['gene_matrices'] = {
+            'genes': [str(g) for g in lista],
+            'jsd': [[float(v) for v in row] for row in c.JSD_matrix(lista)],
+            'cor': [[float(v) for v in row] for row in c.cor_matrix(lista)],
+            'adjacency': [[float(v) for v in row] for row in c.adjacency_matrix(lista)],
+            'adjacency_2': [[float(v) for v in row] for row in c.adjacency_matrix(lista, ind=2)],
+        }
     # the table writer, RNG stream consumed gene by gene from `seed`
     numpy.random.seed(seed)
     c.save(n=n_perm, filtercells=0, filterexp=0.0, annotation={'setA': genes[3:9], 'setB': genes[5:6]})

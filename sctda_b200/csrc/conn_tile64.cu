@@ -66,7 +66,8 @@ __device__ __forceinline__ float pm_fast(double acc, double q, double inv_q, con
     const unsigned lo = (unsigned)__double2loint(y) & 0x1fffffffu;
     const bool clear = (lo - 0x10000000u + kGuard) >= 2u * kGuard;     // away from the rounding boundary
     float f = (float)y;
-    if (!(clear && t >= 0.00390625 && t <= 1e30)) f = pm_log2_value(div_rn(acc, q, inv_q));
+    if (acc == 0.0) f = 0.0f;                                          // an empty node: log1p(0) = 0 (select, no branch)
+    else if (!(clear && t >= 0.00390625 && t <= 1e30)) f = pm_log2_value(div_rn(acc, q, inv_q));
     return f;
 }
 
@@ -90,6 +91,7 @@ struct Tile64Args {
     double* scores;
     float* pm;                  // [grid][V][64]
     unsigned long long* counter;
+    const int* unit_w;          // 1 when all adjacency weights are 1.0
 };
 
 __device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src) {
@@ -104,64 +106,103 @@ __device__ __forceinline__ void cp_async_wait_all() {
 // its sector's bit and loads its two genes under that predicate into registers cleared beforehand
 // (ptxas turns predicated FP64 adds into add + select, which costs more than the clear), then adds
 // them in member order.  The loads come first in program order.
-#define SCTDA_T64_LD(i)                                                        \
-    "and.b32 t, %" #i ", %10;\n setp.ne.u32 p, t, 0;\n"                       \
-    "shr.u32 t, %" #i ", 16;\n mad.wide.u32 ad, t, 512, %11;\n"               \
+#define SCTDA_T64_LD(i, j)                                                     \
+    "and.b32 t, %" #j ", %18;\n setp.ne.u32 p, t, 0;\n"                       \
+    "mad.wide.u32 ad, %" #i ", 16, %19;\n"                                    \
     "mov.f64 a" #i ", 0d0000000000000000;\n mov.f64 b" #i ", 0d0000000000000000;\n" \
     "@p ld.global.nc.v2.f64 {a" #i ", b" #i "}, [ad];\n"
 #define SCTDA_T64_ADD(i) "add.rn.f64 %0, %0, a" #i ";\nadd.rn.f64 %1, %1, b" #i ";\n"
 
-__device__ __forceinline__ void group8(double& acc0, double& acc1, const uint4 wa, const uint4 wb, unsigned lanebit,
-                                       const double* base) {
+// e0..e3: eight list entries (x, z = row offsets in 16-byte units; y, w = sector masks).
+__device__ __forceinline__ void group8(double& acc0, double& acc1, const uint4 e0, const uint4 e1, const uint4 e2,
+                                       const uint4 e3, unsigned lanebit, const double* base) {
     asm volatile(
         "{\n.reg .pred p;\n.reg .b32 t;\n.reg .b64 ad;\n"
         ".reg .f64 a2, a3, a4, a5, a6, a7, a8, a9, b2, b3, b4, b5, b6, b7, b8, b9;\n"
-        SCTDA_T64_LD(2) SCTDA_T64_LD(3) SCTDA_T64_LD(4) SCTDA_T64_LD(5)
-        SCTDA_T64_LD(6) SCTDA_T64_LD(7) SCTDA_T64_LD(8) SCTDA_T64_LD(9)
+        SCTDA_T64_LD(2, 10) SCTDA_T64_LD(3, 11) SCTDA_T64_LD(4, 12) SCTDA_T64_LD(5, 13)
+        SCTDA_T64_LD(6, 14) SCTDA_T64_LD(7, 15) SCTDA_T64_LD(8, 16) SCTDA_T64_LD(9, 17)
         SCTDA_T64_ADD(2) SCTDA_T64_ADD(3) SCTDA_T64_ADD(4) SCTDA_T64_ADD(5)
         SCTDA_T64_ADD(6) SCTDA_T64_ADD(7) SCTDA_T64_ADD(8) SCTDA_T64_ADD(9)
         "}\n"
         : "+d"(acc0), "+d"(acc1)
-        : "r"(wa.x), "r"(wa.y), "r"(wa.z), "r"(wa.w), "r"(wb.x), "r"(wb.y), "r"(wb.z), "r"(wb.w), "r"(lanebit),
-          "l"(base));
+        : "r"(e0.x), "r"(e0.z), "r"(e1.x), "r"(e1.z), "r"(e2.x), "r"(e2.z), "r"(e3.x), "r"(e3.z),
+          "r"(e0.y), "r"(e0.w), "r"(e1.y), "r"(e1.w), "r"(e2.y), "r"(e2.w), "r"(e3.y), "r"(e3.w),
+          "r"(lanebit), "l"(base));
 }
 
 constexpr int kSeg = 64;          // members compacted at a time (two chunks of 32)
 constexpr int kList = kSeg + 8;   // list entries per buffer: up to 64 live members + padding to a multiple of eight
 
-// Composite word of one member: perm[col] in the high half, the sector mask of that cell in the low
-// half; 0 for a lane beyond the segment (a zero mask: never gathered).
-__device__ __forceinline__ unsigned composite(const uint16_t* perm_s, const uint16_t* sec_s, int col, bool valid) {
-    unsigned pk = 0;
+// List entry of one member: x = offset of the gathered row perm[col] in 16-byte units, y = the sector mask of
+// that cell; (0, 0) for a lane beyond the segment (a zero mask is never gathered).
+__device__ __forceinline__ uint2 composite(const uint16_t* perm_s, const uint16_t* sec_s, int col, bool valid) {
+    uint2 pk = make_uint2(0u, 0u);
     if (valid) {
         const unsigned c = perm_s[col];
-        pk = (c << 16) | (unsigned)sec_s[c];
+        pk = make_uint2(c * (unsigned)(kPitch / 2), (unsigned)sec_s[c]);
     }
     return pk;
 }
 
 // Appends the live members (non-zero sector mask) of one chunk of 32 to the list, in member order.
-__device__ __forceinline__ int append_live(unsigned* list, int count, unsigned pk, int lane) {
-    const bool live = (pk & 0xffffu) != 0;
+__device__ __forceinline__ int append_live(uint2* list, int count, uint2 pk, int lane) {
+    const bool live = pk.y != 0;
     const unsigned bal = __ballot_sync(0xffffffffu, live);
     if (live) list[count + __popc(bal & ((1u << lane) - 1u))] = pk;
     return count + __popc(bal);
 }
 
-// Pads the list to a multiple of eight with zero words and makes it visible to the warp.
-__device__ __forceinline__ void close_list(unsigned* list, int count, int lane) {
-    if (lane < 8) list[count + lane] = 0;
+// Pads the list to a multiple of eight with empty entries and makes it visible to the warp.
+__device__ __forceinline__ void close_list(uint2* list, int count, int lane) {
+    if (lane < 8) list[count + lane] = make_uint2(0u, 0u);
     __syncwarp();
 }
 
 // Sequential sums over a compacted list (member order), eight entries per gather round.
-__device__ __forceinline__ void sum_list(double& acc0, double& acc1, const unsigned* list, int count, unsigned lanebit,
+__device__ __forceinline__ void sum_list(double& acc0, double& acc1, const uint2* list, int count, unsigned lanebit,
                                          const double* base) {
     for (int g = 0; g < count; g += 8) {
-        const uint4 wa = *(const uint4*)(list + g), wb = *(const uint4*)(list + g + 4);     // broadcast loads
-        group8(acc0, acc1, wa, wb, lanebit, base);
+        const uint4* q = (const uint4*)(list + g);                                          // broadcast loads
+        group8(acc0, acc1, q[0], q[1], q[2], q[3], lanebit, base);
     }
     __syncwarp();
+}
+
+// s += sum over the first `cnt` (1..8) edges held by lanes 0..cnt-1 of w * pm[l], in edge order.  Exactly
+// cnt row loads and adds are issued (a switch on the warp-uniform count, not predication).
+template <int C, bool UNIT>
+__device__ __forceinline__ void spmv_rows_c(double& s0, double& s1, const float* pm, int li, double lw, int lane) {
+    float2 v[C];
+#pragma unroll
+    for (int u = 0; u < C; ++u) {
+        const int l = __shfl_sync(0xffffffffu, li, u);
+        v[u] = __ldcg((const float2*)(pm + (size_t)l * kT) + lane);
+    }
+#pragma unroll
+    for (int u = 0; u < C; ++u) {
+        if (UNIT) {                                                // weight 1.0: w * x == x exactly
+            s0 += (double)v[u].x;
+            s1 += (double)v[u].y;
+        } else {
+            const double wt = __shfl_sync(0xffffffffu, lw, u);
+            s0 += wt * (double)v[u].x;
+            s1 += wt * (double)v[u].y;
+        }
+    }
+}
+
+template <bool UNIT>
+__device__ __forceinline__ void spmv_rows(double& s0, double& s1, const float* pm, int li, double lw, int cnt, int lane) {
+    switch (cnt) {
+        case 1: spmv_rows_c<1, UNIT>(s0, s1, pm, li, lw, lane); break;
+        case 2: spmv_rows_c<2, UNIT>(s0, s1, pm, li, lw, lane); break;
+        case 3: spmv_rows_c<3, UNIT>(s0, s1, pm, li, lw, lane); break;
+        case 4: spmv_rows_c<4, UNIT>(s0, s1, pm, li, lw, lane); break;
+        case 5: spmv_rows_c<5, UNIT>(s0, s1, pm, li, lw, lane); break;
+        case 6: spmv_rows_c<6, UNIT>(s0, s1, pm, li, lw, lane); break;
+        case 7: spmv_rows_c<7, UNIT>(s0, s1, pm, li, lw, lane); break;
+        default: spmv_rows_c<8, UNIT>(s0, s1, pm, li, lw, lane); break;
+    }
 }
 
 template <int NW>
@@ -172,13 +213,14 @@ __global__ void __launch_bounds__(NW * 32, 1) conn_perm64_kernel(Tile64Args a) {
     double2* s_tab = (double2*)(s_sec + a.Sp);                    // [128]
     double* s_tot = (double*)(s_tab + 128);                       // [NW][64]
     double* s_part = s_tot + NW * kT;                             // [NW][64]
-    unsigned* s_list = (unsigned*)(s_part + NW * kT);             // [NW][2][kList] compacted composite words
+    uint2* s_list = (uint2*)(s_part + NW * kT);                   // [NW][2][kList] compacted list entries
     __shared__ long long s_claim[2];
     const int lane = threadIdx.x & 31;
     const int w = threadIdx.x >> 5;
-    const unsigned lanebit = 1u << (lane >> 1);
+    const unsigned lanebit = 1u << (lane >> 1);                   // this lane's sector in a mask
     float* pm = a.pm + (size_t)blockIdx.x * a.V * kT;
     const double cor = (double)a.V / (double)(a.V - 1);           // ref:989
+    const bool unit_w = *a.unit_w != 0;                           // every edge weight is exactly 1.0
     const int chunks16 = a.Sp >> 3;                               // 16-byte pieces of a row
     for (int i = threadIdx.x; i < 128; i += NW * 32) s_tab[i] = g_logtab[i];
     if (threadIdx.x == 0) {
@@ -223,7 +265,7 @@ __global__ void __launch_bounds__(NW * 32, 1) conn_perm64_kernel(Tile64Args a) {
             // The list of node k+NW is built while node k is summed: its member columns are fetched
             // before the sums and turned into composite words after them.
             double tot0 = 0.0, tot1 = 0.0;
-            unsigned* lst = s_list + (size_t)w * 2 * kList;
+            uint2* lst = s_list + (size_t)w * 2 * kList;
             int cur = 0;
             int k = w, beg = 0, end = 0, count = 0;
             if (k < a.V) {
@@ -250,7 +292,7 @@ __global__ void __launch_bounds__(NW * 32, 1) conn_perm64_kernel(Tile64Args a) {
                 double acc0 = 0.0, acc1 = 0.0;
                 sum_list(acc0, acc1, lst + cur * kList, count, lanebit, base);
                 for (int sb = beg + kSeg; sb < end; sb += kSeg) {  // nodes above 64 members: further segments, in order
-                    unsigned* l2 = lst + cur * kList;
+                    uint2* l2 = lst + cur * kList;
                     const int ns = min(kSeg, end - sb);
                     const int c0 = lane < ns ? __ldg(a.node_cols + sb + lane) : 0;
                     const int c1 = lane + 32 < ns ? __ldg(a.node_cols + sb + 32 + lane) : 0;
@@ -272,7 +314,7 @@ __global__ void __launch_bounds__(NW * 32, 1) conn_perm64_kernel(Tile64Args a) {
                 tot0 += (double)pv.x;                              // ref:984
                 tot1 += (double)pv.y;
                 if (kn < a.V) {
-                    unsigned* l2 = lst + (cur ^ 1) * kList;
+                    uint2* l2 = lst + (cur ^ 1) * kList;
                     count = append_live(l2, 0, composite(perm_r, s_sec, cn0, lane < nn), lane);
                     if (nn > 32) count = append_live(l2, count, composite(perm_r, s_sec, cn1, lane + 32 < nn), lane);
                     close_list(l2, count, lane);
@@ -284,20 +326,57 @@ __global__ void __launch_bounds__(NW * 32, 1) conn_perm64_kernel(Tile64Args a) {
             s_tot[w * kT + 2 * lane + 1] = tot1;
             __syncthreads();
             // ---- p'Ap on the un-normalised values; the 1/tot^2 is applied once (ref:988-989) ----
+            // One adjacency row per step, its (up to eight) node rows in flight together, the sums in edge
+            // order; the edge indices of the next row are fetched while the current one is summed.
             double part0 = 0.0, part1 = 0.0;
-            for (int kk = w; kk < a.V; kk += NW) {
-                const int eb = __ldg(a.adj_off + kk), ee = __ldg(a.adj_off + kk + 1);
-                double s0 = 0.0, s1 = 0.0;
-                for (int e = eb; e < ee; ++e) {
-                    const int l = __ldg(a.adj_idx + e);
-                    const double wt = __ldg(a.adj_w + e);
-                    const float2 v = __ldcg((const float2*)(pm + (size_t)l * kT) + lane);
-                    s0 += wt * (double)v.x;
-                    s1 += wt * (double)v.y;
+            {
+                int kk = w, eb = 0, ee = 0, ebn = 0, een = 0, li = 0;
+                double lw = 0.0;
+                if (kk < a.V) {
+                    eb = __ldg(a.adj_off + kk);
+                    ee = __ldg(a.adj_off + kk + 1);
+                    if (lane < min(8, ee - eb)) {
+                        li = __ldg(a.adj_idx + eb + lane);
+                        if (!unit_w) lw = __ldg(a.adj_w + eb + lane);
+                    }
                 }
-                const float2 vk = __ldcg((const float2*)(pm + (size_t)kk * kT) + lane);
-                part0 += (double)vk.x * s0;
-                part1 += (double)vk.y * s1;
+                if (kk + NW < a.V) {
+                    ebn = __ldg(a.adj_off + kk + NW);
+                    een = __ldg(a.adj_off + kk + NW + 1);
+                }
+                while (kk < a.V) {
+                    const int kn = kk + NW, k2 = kk + 2 * NW;
+                    int lin = 0, eb2 = 0, ee2 = 0;
+                    double lwn = 0.0;
+                    if (kn < a.V && lane < min(8, een - ebn)) {    // next row's first edges
+                        lin = __ldg(a.adj_idx + ebn + lane);
+                        if (!unit_w) lwn = __ldg(a.adj_w + ebn + lane);
+                    }
+                    if (k2 < a.V) {                                // offsets two rows ahead
+                        eb2 = __ldg(a.adj_off + k2);
+                        ee2 = __ldg(a.adj_off + k2 + 1);
+                    }
+                    double s0 = 0.0, s1 = 0.0;
+                    if (ee > eb) {
+                        const float2 vk = __ldcg((const float2*)(pm + (size_t)kk * kT) + lane);
+                        if (unit_w) spmv_rows<true>(s0, s1, pm, li, lw, min(8, ee - eb), lane);
+                        else spmv_rows<false>(s0, s1, pm, li, lw, min(8, ee - eb), lane);
+                        for (int e0 = eb + 8; e0 < ee; e0 += 8) {  // rows with more than eight edges
+                            const int cnt = min(8, ee - e0);
+                            int l2 = 0;
+                            double w2 = 0.0;
+                            if (lane < cnt) {
+                                l2 = __ldg(a.adj_idx + e0 + lane);
+                                if (!unit_w) w2 = __ldg(a.adj_w + e0 + lane);
+                            }
+                            if (unit_w) spmv_rows<true>(s0, s1, pm, l2, w2, cnt, lane);
+                            else spmv_rows<false>(s0, s1, pm, l2, w2, cnt, lane);
+                        }
+                        part0 += (double)vk.x * s0;
+                        part1 += (double)vk.y * s1;
+                    }
+                    kk = kn; eb = ebn; ee = een; ebn = eb2; een = ee2; li = lin; lw = lwn;
+                }
             }
             s_part[w * kT + 2 * lane] = part0;
             s_part[w * kT + 2 * lane + 1] = part1;
@@ -402,6 +481,13 @@ __global__ void inv_size64_kernel(const int32_t* __restrict__ off, int V, double
     if (k < V) inv_q[k] = 1.0 / (double)(off[k + 1] - off[k]);
 }
 
+// *flag (preset to 1) is cleared when an edge weight differs from 1.0
+__global__ void unit_weight_kernel(const int32_t* __restrict__ adj_off, int V, const double* __restrict__ w, int* flag) {
+    const int nnz = adj_off[V];
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += gridDim.x * blockDim.x)
+        if (w[e] != 1.0) *flag = 0;
+}
+
 // pm_fast against the full-accuracy path on pseudo-random sums and node sizes.
 __global__ void selftest_pm_fast_kernel(int64_t n, uint64_t seed, unsigned long long* out) {
     __shared__ double2 tab[128];
@@ -451,7 +537,7 @@ int launch64(sctda_ctx* ctx, const Tile64Args& a, int grid, size_t smem, cudaStr
 
 // Shared-memory bytes the 64-gene kernel needs for S cells with NW warps.
 static size_t tile64_smem(int Sp, int NW) {
-    return (size_t)3 * Sp * 2 + 128 * sizeof(double2) + (size_t)2 * NW * kT * sizeof(double) + (size_t)NW * 2 * kList * sizeof(unsigned);
+    return (size_t)3 * Sp * 2 + 128 * sizeof(double2) + (size_t)2 * NW * kT * sizeof(double) + (size_t)NW * 2 * kList * sizeof(uint2);
 }
 
 static int tile64_warps() {
@@ -492,7 +578,12 @@ int sctda_conn_perm_tile64(sctda_ctx* ctx, const sctda_graph* gr, int G, const d
     double* inv_q = (double*)sctda_ws(ctx, WS_MISC, (size_t)gr->V * sizeof(double) + 64);
     if (!inv_q) return SCTDA_ERR_NOMEM;
     unsigned long long* counter = (unsigned long long*)(inv_q + gr->V);
+    int* unit_w = (int*)(counter + 1);
+    const int one = 1;
     SCTDA_CUDA(ctx, cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
+    SCTDA_CUDA(ctx, cudaMemcpyAsync(unit_w, &one, sizeof(int), cudaMemcpyHostToDevice, st));
+    unit_weight_kernel<<<64, 256, 0, st>>>(gr->d_adj_off, gr->V, gr->d_adj_w, unit_w);
+    SCTDA_LAUNCH_CHECK(ctx, "unit_weight_kernel");
     identity_gmap_kernel<<<(tiles * kT + 255) / 256, 256, 0, st>>>(gmap, d_order, G, tiles * kT);
     SCTDA_LAUNCH_CHECK(ctx, "identity_gmap_kernel");
     if (Sp != gr->S) SCTDA_CUDA(ctx, cudaMemsetAsync(sec, 0, (size_t)tiles * Sp * sizeof(uint16_t), st));
@@ -512,19 +603,53 @@ int sctda_conn_perm_tile64(sctda_ctx* ctx, const sctda_graph* gr, int G, const d
     a.adj_off = gr->d_adj_off; a.adj_idx = gr->d_adj_idx; a.adj_w = gr->d_adj_w;
     a.ET = ET; a.sec = sec; a.perm16 = perm16; a.gmap = gmap; a.inv_q = inv_q;
     a.observed = d_observed; a.tie_rel = tie_rel > 0.0 ? tie_rel : 1e-9;
-    a.exceed = d_exceed; a.ties = d_ties; a.scores = d_scores; a.counter = counter;
+    a.exceed = d_exceed; a.ties = d_ties; a.scores = d_scores; a.counter = counter; a.unit_w = unit_w;
     long long grid64 = ctx->sm_count;                              // one CTA per SM
+    if (const char* e = getenv("SCTDA_CONN64_GRID")) grid64 = atoi(e) > 0 ? atoi(e) : grid64;
     if (grid64 > a.items) grid64 = a.items;
     const int grid = (int)grid64;
     a.pm = (float*)sctda_ws(ctx, WS_PM, (size_t)grid * gr->V * kT * sizeof(float));
     if (!a.pm) return SCTDA_ERR_NOMEM;
     const int NW = tile64_warps();
     const size_t smem = tile64_smem(Sp, NW);
+    // The node-value scratch (grid x V x 64 float32, 76 MB at V = 2,000) is written and re-read by its CTA
+    // for every permutation; next to the gene tile it overflows what the L2 keeps under plain LRU (measured:
+    // hit rate 65 %, every scratch line fetched from DRAM).  It is marked persisting for this launch.
+    static const bool no_persist = getenv("SCTDA_CONN64_PERSIST") == nullptr;     // measured slower (19.2 vs 16.3 ms): off unless asked for
+    const size_t pm_bytes = (size_t)grid * gr->V * kT * sizeof(float);
+    bool window = false;
+    if (!no_persist) {
+        int max_persist = 0, max_window = 0;
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, ctx->device);
+        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, ctx->device);
+        if (max_persist > 0 && max_window > 0) {
+            if (!(ctx->attr_done & 0x200u)) {
+                cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist);
+                ctx->attr_done |= 0x200u;
+            }
+            cudaStreamAttrValue av;
+            memset(&av, 0, sizeof(av));
+            av.accessPolicyWindow.base_ptr = (void*)a.pm;
+            av.accessPolicyWindow.num_bytes = pm_bytes < (size_t)max_window ? pm_bytes : (size_t)max_window;
+            const double ratio = (double)max_persist / (double)av.accessPolicyWindow.num_bytes;
+            av.accessPolicyWindow.hitRatio = ratio < 1.0 ? (float)ratio : 1.0f;
+            av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            av.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+            window = cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av) == cudaSuccess;
+            cudaGetLastError();
+        }
+    }
     SCTDA_TIME_BEGIN(ctx, st);
     if (NW == 16) rc = launch64<16>(ctx, a, grid, smem, st);
     else if (NW == 32) rc = launch64<32>(ctx, a, grid, smem, st);
     else rc = launch64<24>(ctx, a, grid, smem, st);
     SCTDA_TIME_END(ctx, st);
+    if (window) {                                                  // later launches on this stream: no window
+        cudaStreamAttrValue av;
+        memset(&av, 0, sizeof(av));
+        cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av);
+        cudaGetLastError();
+    }
     if (rc) return rc;
     SCTDA_LAUNCH_CHECK(ctx, "conn_perm64_kernel");
     return SCTDA_OK;

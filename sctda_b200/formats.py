@@ -50,22 +50,40 @@ def _to_float_column(strings):
     return out, ok
 
 
-def write_table_sidecar(path, names, Y, cell_id=(), libs=(), cdr=None):
+def _table_fingerprint(path):
+    import os
+    st = os.stat(path)
+    return numpy.array([st.st_size, st.st_mtime_ns], dtype=numpy.int64)
+
+
+def write_table_sidecar(path, names, Y, cell_id=(), libs=(), cdr=None, csv=False):
     """Binary side-car `<table>.npz` of an expression table: the TSV stays the
-    interchange format of the reference; when the side-car is present and newer than the TSV,
-    read_table loads it instead of parsing 10^8-10^9 text fields in Python."""
-    numpy.savez(path + '.npz', names=numpy.array(list(names), dtype=object), Y=numpy.asarray(Y, dtype=numpy.float64),
-                cell_id=numpy.array(list(cell_id), dtype=object), libs=numpy.array(list(libs), dtype=object),
-                cdr=numpy.zeros(0) if cdr is None else numpy.asarray(cdr, dtype=numpy.float64))
+    interchange format of the reference; read_table loads the side-car instead of parsing 10^8-10^9
+    text fields when it was written for exactly this file (size and mtime of the table are recorded)
+    and for the same `csv` flag.  Strings are stored as fixed-width unicode arrays: nothing in the
+    file is a pickle."""
+    numpy.savez(path + '.npz', names=numpy.array(list(names), dtype=numpy.str_),
+                Y=numpy.asarray(Y, dtype=numpy.float64), cell_id=numpy.array(list(cell_id), dtype=numpy.str_),
+                libs=numpy.array(list(libs), dtype=numpy.str_),
+                cdr=numpy.zeros(0) if cdr is None else numpy.asarray(cdr, dtype=numpy.float64),
+                table=_table_fingerprint(path), csv=numpy.array([1 if csv else 0], dtype=numpy.int64))
 
 
-def _read_sidecar(path):
+def _read_sidecar(path, csv=False):
     import os
     side = path + '.npz'
-    if not os.path.exists(side) or os.path.getmtime(side) < os.path.getmtime(path):
+    if not os.path.exists(side):
         return None
-    z = numpy.load(side, allow_pickle=True)
-    return list(z['names']), numpy.ascontiguousarray(z['Y']), list(z['cell_id']), list(z['libs']), z['cdr']
+    try:
+        z = numpy.load(side, allow_pickle=False)
+        if 'table' not in z.files or 'csv' not in z.files:
+            return None
+        if not (z['table'] == _table_fingerprint(path)).all() or int(z['csv'][0]) != (1 if csv else 0):
+            return None                                   # written for another version of the table
+        return ([str(x) for x in z['names']], numpy.ascontiguousarray(z['Y']), [str(x) for x in z['cell_id']],
+                [str(x) for x in z['libs']], z['cdr'])
+    except (ValueError, OSError, KeyError):
+        return None                                       # not one of ours (e.g. an object array): parse the text
 
 
 def _parse_native(path, csv):
@@ -124,7 +142,7 @@ def read_table(path, shift=None, csv=False, sidecar=True, native=True):
     cell_id / libs  the non-numeric fields of column 0 / column 'lib' (shift=None only),
     cdr     fraction of columns with value > 0 per cell, excluding ID / lib / timepoint."""
     if sidecar and shift is None:
-        got = _read_sidecar(path)
+        got = _read_sidecar(path, csv)
         if got is not None:
             return got
     got = _parse_native(path, csv) if native else None

@@ -20,6 +20,7 @@ import torch
 
 from . import _lib
 from . import formats
+from . import geneorder
 
 
 def benjamini_hochberg(pvalues):
@@ -56,7 +57,7 @@ def reference_perm_indices(n, S, rng=None):
     rc = lib.sctda_mt19937_shuffle_rows(key.ctypes.data, ctypes.byref(pos), int(n), int(S), out.ctypes.data)
     if rc != 0:
         raise _lib.SctdaError(rc, 'sctda_mt19937_shuffle_rows')
-    (numpy.random if rng is None else rng).set_state((st[0], key, int(pos.value), 0, 0.0))
+    (numpy.random if rng is None else rng).set_state((st[0], key, int(pos.value), st[3], st[4]))   # shuffle leaves a cached normal deviate alone
     return out
 
 
@@ -69,12 +70,17 @@ class DeviceGraph(object):
         dev = torch.device('cuda', device)
         samples = numpy.asarray(samples, dtype=numpy.int64)
         V = len(node_members)
+        if samples.size and (int(samples.min()) < 0 or int(samples.max()) >= int(n_cells)):
+            raise ValueError('samples must be table rows in [0, %d): got [%d, %d] (name.json and the table disagree; '
+                             'the reference raises IndexError here)' % (n_cells, samples.min(), samples.max()))
         pos = numpy.full(int(samples.max()) + 1 if samples.size else 1, -1, dtype=numpy.int64)
         pos[samples] = numpy.arange(samples.size)                     # koi of ref:973-974
         sizes = numpy.array([len(m) for m in node_members], dtype=numpy.int64)
         off = numpy.zeros(V + 1, dtype=numpy.int64)
         numpy.cumsum(sizes, out=off[1:])
         flat = numpy.concatenate([numpy.asarray(m, dtype=numpy.int64) for m in node_members]) if V else numpy.zeros(0, numpy.int64)
+        if flat.size and (int(flat.min()) < 0 or int(flat.max()) >= pos.size):
+            raise ValueError('node member lists must be non-empty and contained in samples')
         cols = pos[flat]
         if (cols < 0).any() or (sizes == 0).any():
             raise ValueError('node member lists must be non-empty and contained in samples')
@@ -163,6 +169,21 @@ def conn_perm_test(ctx, dg, Y, perms, observed, log2=True, per_gene=False, want_
     return exceed, ties, scores
 
 
+def check_permutation_block(perms, S):
+    """A user-supplied shared block must be [n, S] with every row a permutation of arange(S): the kernels
+    gather table rows through these indices without bounds checks."""
+    perms = numpy.asarray(perms)
+    if perms.ndim != 2 or perms.shape[1] != S:
+        raise ValueError('perms must be [n, %d] (one row of cell positions per permutation), got %r' % (S, perms.shape))
+    if perms.size:
+        if int(perms.min()) < 0 or int(perms.max()) >= S:
+            raise ValueError('perms entries must lie in [0, %d)' % S)
+        srt = numpy.sort(perms, axis=1)
+        if not (srt == numpy.arange(S, dtype=srt.dtype)[None, :]).all():
+            raise ValueError('every row of perms must be a permutation of arange(%d)' % S)
+    return perms
+
+
 def conn_perm_test_host(ctx, dg, Y_host, perms_host, observed_host, log2=True):
     """The permutation test on HOST buffers (pinned torch tensors or numpy arrays): copies the
     table, the shared permutation block and the observed scores to the device, runs
@@ -172,7 +193,8 @@ def conn_perm_test_host(ctx, dg, Y_host, perms_host, observed_host, log2=True):
     Yd = torch.as_tensor(Y_host).to(dev, non_blocking=True)
     pd = torch.as_tensor(perms_host).to(dev, non_blocking=True)
     od = torch.as_tensor(observed_host).to(dev, non_blocking=True)
-    ex, _, _ = conn_perm_test(ctx, dg, Yd, pd, od, log2=log2, per_gene=(pd.dim() == 3))
+    order = geneorder.gene_order(Yd) if pd.dim() == 2 else None        # tile layout of the shared-block kernel
+    ex, _, _ = conn_perm_test(ctx, dg, Yd, pd, od, log2=log2, per_gene=(pd.dim() == 3), gene_order=order)
     out = torch.empty(ex.shape, dtype=ex.dtype, pin_memory=True)
     out.copy_(ex, non_blocking=True)
     torch.cuda.current_stream(dev).synchronize()
@@ -369,8 +391,13 @@ class UnrootedGraph(object):
         if len(genes) == 0 or n == 0:
             return (list(pvals), ties) if return_ties else list(pvals)
         if perms is not None:
+            perms = check_permutation_block(perms, dg.S)
+            if int(perms.shape[0]) != int(n):
+                raise ValueError('perms has %d rows but n = %d: pass n = perms.shape[0] (the p-value is the exceed '
+                                 'count over the number of permutations applied)' % (perms.shape[0], n))
             pd = torch.as_tensor(numpy.ascontiguousarray(perms, dtype=numpy.int32)).to(dev)
-            ex, ti, _ = conn_perm_test(ctx, dg, Yd.index_select(0, self._rows(genes)), pd, obs_all, log2=self.log2)
+            Ysel = Yd.index_select(0, self._rows(genes))
+            ex, ti, _ = conn_perm_test(ctx, dg, Ysel, pd, obs_all, log2=self.log2, gene_order=geneorder.gene_order(Ysel))
             pvals = ex.cpu().numpy() / float(n)
             ties = ti.cpu().numpy()
         else:
@@ -448,12 +475,16 @@ class UnrootedGraph(object):
             rows.append(row)
         return header, rows
 
-    def save(self, n=500, filtercells=0, filterexp=0.0, annotation={}, perms=None):
-        """ref:1053-1086: writes name.genes.tsv (the scatter plot of ref:1087-1109 is not
-        produced).  perms: see connectivity_pvalues.  Returns (header, rows)."""
-        header, rows = self._table_rows(n, filtercells, filterexp, annotation, False, perms)
+    def table(self, n=500, filtercells=0, filterexp=0.0, annotation={}, perms=None):
+        """(header, rows) of the gene table save() writes, without writing it."""
+        return self._table_rows(n, filtercells, filterexp, annotation, isinstance(self, RootedGraph), perms)
+
+    def save(self, n=500, filtercells=0, filterexp=0.0, annotation={}, *, perms=None):
+        """ref:1053-1086: writes name.genes.tsv and returns None, as the reference does (the scatter
+        plot of ref:1087-1109 is not produced; the rows stay available as self.last_table).  `perms` (keyword only, an
+        extension): see connectivity_pvalues."""
+        header, rows = self.last_table = self.table(n, filtercells, filterexp, annotation, perms)
         formats.write_genes_tsv(self.name + '.genes.tsv', header, rows)
-        return header, rows
 
 
 class RootedGraph(UnrootedGraph):
@@ -516,17 +547,20 @@ class RootedGraph(UnrootedGraph):
 
     @staticmethod
     def find_root(dendritem):
-        """ref:1481-1497."""
-        q, q2 = 1000.0, -1000.0
-        ind, ind2 = 0, 0
-        for nn in dendritem.keys():
-            if -2.0 < dendritem[nn] < q:
-                q = dendritem[nn]
-                ind = nn
-            if dendritem[nn] > q2 and dendritem[nn] > -2.0:
-                q2 = dendritem[nn]
-                ind2 = nn
-        return ind, ind2
+        """ref:1481-1497: (root, leaf) = the nodes with the smallest and the largest score among the
+        scores above -2 (NaN scores never qualify), the first such node in dictionary order on ties;
+        the reference's sentinels are kept: no score below 1000 leaves root = 0, none above -1000
+        leaves leaf = 0."""
+        keys = list(dendritem.keys())
+        if not keys:
+            return 0, 0
+        v = numpy.array([dendritem[k] for k in keys], dtype=numpy.float64)
+        ok = v > -2.0
+        lo = numpy.where(ok & (v < 1000.0), v, numpy.inf)
+        hi = numpy.where(ok & (v > -1000.0), v, -numpy.inf)
+        root = keys[int(numpy.argmin(lo))] if numpy.isfinite(lo).any() else 0
+        leaf = keys[int(numpy.argmax(hi))] if numpy.isfinite(hi).any() else 0
+        return root, leaf
 
     def _centroid_from_raw(self, cen, disp):
         if numpy.isnan(cen):
@@ -547,8 +581,7 @@ class RootedGraph(UnrootedGraph):
         i = self.gene_row[genin]
         return self._centroid_from_raw(s['cen'][i], s['disp'][i])
 
-    def save(self, n=500, filtercells=0, filterexp=0.0, annotation={}, perms=None):
-        """ref:1879-1914."""
-        header, rows = self._table_rows(n, filtercells, filterexp, annotation, True, perms)
+    def save(self, n=500, filtercells=0, filterexp=0.0, annotation={}, *, perms=None):
+        """ref:1879-1914: as UnrootedGraph.save with the Centroid and Dispersion columns; returns None."""
+        header, rows = self.last_table = self.table(n, filtercells, filterexp, annotation, perms)
         formats.write_genes_tsv(self.name + '.genes.tsv', header, rows)
-        return header, rows

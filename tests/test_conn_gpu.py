@@ -162,7 +162,8 @@ def test_golden_reference_vectors(golden_dir, tmp_path, name):
     # the table writer, RNG stream consumed gene by gene from `seed` (ref:1068-1071)
     genes = sorted(c.gene_row.keys())
     numpy.random.seed(ref['seed'])
-    header, rows = c.save(n=n, annotation={'setA': genes[3:9], 'setB': genes[5:6]})
+    assert c.save(n=n, annotation={'setA': genes[3:9], 'setB': genes[5:6]}) is None       # ref:1053-1109 returns nothing
+    header, rows = c.last_table
     with open(os.path.join(golden_dir, name + '.ref.genes.tsv')) as f:
         gold = [l[:-1].split('\t') for l in f]
     with open(prefix + '.genes.tsv') as f:
@@ -327,6 +328,25 @@ def test_gene_gene_matrices(golden_dir, tmp_path):
     numpy.testing.assert_allclose(c.adjacency_matrix(genes[:5], ind=2), co.adjacency_matrix(st, genes[:5], ind=2), rtol=1e-11, atol=0)
     sel = [g for g in genes if numpy.std(c.dicgenes[g]) > 0]         # a constant gene has no correlation distance
     numpy.testing.assert_allclose(c.cor_matrix(sel), co.cor_matrix(st, sel), rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.parametrize('name', ['unrooted_a', 'rooted_b'])
+def test_gene_gene_matrices_match_reference_golden(golden_dir, tmp_path, name):
+    """The product's JSD_matrix / cor_matrix / adjacency_matrix against the matrices the reference's own
+    methods (ref:1111-1190) returned when its source was run on these files (oracle/gen_golden.py)."""
+    _gpu()
+    from sctda_b200 import graph
+    for ext in ('.gexf', '.json', '.all.tsv'):
+        shutil.copy(os.path.join(golden_dir, name + ext), str(tmp_path / (name + ext)))
+    with open(os.path.join(golden_dir, name + '.ref.json')) as f:
+        ref = json.load(f)['gene_matrices']
+    prefix = str(tmp_path / name)
+    c = graph.UnrootedGraph(prefix, prefix + '.all.tsv', groups=False)
+    genes = ref['genes']
+    numpy.testing.assert_allclose(c.JSD_matrix(genes) ** 2, numpy.array(ref['jsd']) ** 2, rtol=1e-9, atol=1e-13)
+    numpy.testing.assert_allclose(c.cor_matrix(genes), numpy.array(ref['cor']), rtol=1e-9, atol=1e-12)
+    numpy.testing.assert_allclose(c.adjacency_matrix(genes), numpy.array(ref['adjacency']), rtol=1e-11, atol=0)
+    numpy.testing.assert_allclose(c.adjacency_matrix(genes, ind=2), numpy.array(ref['adjacency_2']), rtol=1e-11, atol=0)
 
 
 @pytest.mark.parametrize('n_cells', [30000, 60000])

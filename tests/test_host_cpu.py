@@ -119,8 +119,16 @@ def test_table_sidecar_round_trip(golden_dir, tmp_path):
     assert n2 == names and list(c2) == list(cell_id) and list(l2) == list(libs)
     numpy.testing.assert_array_equal(Y2, Y)
     numpy.testing.assert_array_equal(cdr2, cdr)
-    # a TSV newer than its side-car wins
-    os.utime(path + '.npz', (1, 1))
+    assert formats._read_sidecar(path) is not None
+    assert formats._read_sidecar(path, csv=True) is None            # written for the tab-separated reading
+    # a table rewritten after its side-car (other size or mtime) is parsed again
+    os.utime(path, ns=(1, 1))
+    assert formats._read_sidecar(path) is None
+    # a side-car that holds pickled objects is never loaded
+    formats.write_table_sidecar(path, names, Y, cell_id, libs, cdr)
+    numpy.savez(path + '.npz', names=numpy.array(names, dtype=object), Y=Y, table=formats._table_fingerprint(path),
+                csv=numpy.array([0]), cell_id=numpy.array(cell_id, dtype=object), libs=numpy.array(libs, dtype=object),
+                cdr=cdr)
     assert formats._read_sidecar(path) is None
 
 

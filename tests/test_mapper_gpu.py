@@ -140,6 +140,81 @@ def test_graph_identical_to_oracle(case):
     assert [tuple(e) for e in res.edges.cpu().numpy().tolist()] == edges
 
 
+def test_graph_identical_to_oracle_5k_cells():
+    """A build the size of a real patch workload against the oracle: 5,000 cells x 500 genes, r = 8,
+    gain 1 (64 patches of ~300 cells; the oracle's C Gram helper keeps it to seconds): node lists
+    and edges identical."""
+    from oracle import mapper_oracle as mo
+    ctx = _gpu()
+    X, lens = _data(5000, 500, seed=77)
+    for metric in ('euclidean', 'correlation'):
+        res = _device_result(ctx, X, lens, 8, 1.0, True, metric, 5, 'db')
+        edges, clusters, _ = mo.mapper_graph(X, lens, 8, 1.0, metric=metric)
+        node_off = res.node_off.cpu().numpy()
+        node_members = res.node_members.cpu().numpy()
+        assert res.V == len(clusters)
+        for k, c in enumerate(clusters):
+            assert list(node_members[node_off[k]:node_off[k + 1]]) == list(c)
+        assert [tuple(e) for e in res.edges.cpu().numpy().tolist()] == edges
+
+
+def test_graph_against_sklearn_single_linkage_and_davies_bouldin():
+    """The whole graph against an INDEPENDENT restatement that shares nothing with the device arithmetic
+    (no Gram trick, no fma chain, no lane-ordered sums): BASELINE.json configs[0]'s scale (1,000 cells x
+    2,000 genes, r = 20, gain 2).  Per patch: sklearn.cluster.AgglomerativeClustering(linkage='single')
+    on the feature rows for K = 2..K_max, K chosen by sklearn.metrics.davies_bouldin_score (smallest
+    index, first K on ties), clusters numbered by smallest member; nerve by set intersection.
+    The clusterings agree wherever the model selection is not decided by the last bits: node sets
+    must match on all patches but a handful, and the graphs must be isomorphic there."""
+    import sklearn.cluster
+    import sklearn.metrics
+    from sctda_b200 import mapper
+    ctx = _gpu()
+    X, lens = _data(1000, 2000, seed=5)
+    r, gain, max_K = 20, 2.0, 5
+    res = _device_result(ctx, X, lens, r, gain, True, 'euclidean', max_K, 'db')
+    bin_off = res.bin_off.cpu().numpy()
+    members = res.members.cpu().numpy()
+    labels = res.labels.cpu().numpy()
+    bin_K = res.bin_K.cpu().numpy()
+    bin_db = res.bin_db.cpu().numpy()
+    lo0, hi0, lo1, hi1 = mapper.cover_bounds(lens, r, gain, True)
+    n_patch = n_same = n_close = 0
+    for b in range(r * r):
+        i, j = divmod(b, r)
+        cells = numpy.nonzero((lens[:, 0] > lo0[i]) & (lens[:, 0] < hi0[i]) & (lens[:, 1] > lo1[j]) & (lens[:, 1] < hi1[j]))[0]
+        assert list(members[bin_off[b]:bin_off[b + 1]]) == list(cells)               # the cover, by brute force
+        m = len(cells)
+        if m < 2:
+            assert bin_K[b] == m
+            continue
+        if m == 2:                              # sklearn's index needs fewer clusters than cells: two singletons
+            assert bin_K[b] == 2
+            continue
+        n_patch += 1
+        kmax = 2 if m <= 5 else min(m // 2, max_K)
+        best = None
+        scores = []
+        for K in range(2, kmax + 1):
+            lab = sklearn.cluster.AgglomerativeClustering(n_clusters=K, linkage='single').fit_predict(X[cells])
+            sc = sklearn.metrics.davies_bouldin_score(X[cells], lab)
+            scores.append(sc)
+            if best is None or sc < best[0]:
+                best = (sc, K, lab)
+        mine = labels[bin_off[b]:bin_off[b + 1]]
+        part_ref = sorted(sorted(int(c) for c in cells[best[2] == k]) for k in range(best[1]))
+        part_me = sorted(sorted(int(c) for c in cells[mine == k]) for k in range(bin_K[b]))
+        numpy.testing.assert_allclose(bin_db[b, :len(scores)], scores, rtol=1e-5)    # the index itself, every K (the
+        # device forms centroid distances from the Gram tile: cancellation costs a few digits, 2e-7 at worst here)
+        if part_ref == part_me:
+            n_same += 1
+        else:                                                                         # two K within rounding of each other
+            srt = sorted(scores)
+            assert srt[1] - srt[0] <= 1e-9 * abs(srt[0]), (b, scores, bin_K[b], best[1])
+            n_close += 1
+    assert n_patch > 200 and n_same >= n_patch - 3
+
+
 def test_topological_representation_files(tmp_path):
     """The reference-facing classes end to end: .mapper.tsv -> TopologicalRepresentation.save ->
     name.json / name.gexf -> UnrootedGraph (ref:735-778, 785-806)."""

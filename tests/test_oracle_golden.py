@@ -126,3 +126,20 @@ def test_py2_str():
     assert co.py2_str(1e-20) == '1e-20'
     assert co.py2_str(3.0) == '3.0'
     assert co.py2_str(None) == 'None'
+
+
+@pytest.mark.parametrize('name', ['unrooted_a', 'rooted_b'])
+def test_gene_gene_matrices_match_reference(golden_dir, name):
+    """The oracle's JSD / correlation / adjacency matrices against the matrices the reference's own
+    JSD_matrix, cor_matrix and adjacency_matrix (ref:1111-1190) returned under the shim."""
+    with open(os.path.join(golden_dir, name + '.ref.json')) as f:
+        ref = json.load(f)['gene_matrices']
+    prefix = os.path.join(golden_dir, name)
+    st = co.load_state(prefix, prefix + '.all.tsv')
+    genes = ref['genes']
+    jsd, _ = co.jsd_matrix(st, genes)
+    numpy.testing.assert_allclose(jsd, numpy.array(ref['jsd']), rtol=1e-9, atol=1e-7)     # sqrt near 0 amplifies the last bits
+    numpy.testing.assert_allclose(co.cor_matrix(st, genes), numpy.array(ref['cor']), rtol=1e-12, atol=1e-14)
+    numpy.testing.assert_allclose(co.adjacency_matrix(st, genes), numpy.array(ref['adjacency']), rtol=1e-12, atol=0)
+    numpy.testing.assert_allclose(co.adjacency_matrix(st, genes, ind=2), numpy.array(ref['adjacency_2']), rtol=1e-12, atol=0)
+

@@ -32,7 +32,11 @@ def main():
     ap.add_argument('--resolution', type=int, default=20)
     ap.add_argument('--gain', type=float, default=2.0)
     ap.add_argument('--oracle', action='store_true')
-    a = ap.parse_args()
+    print(json.dumps(run(ap.parse_args())))
+
+
+def run(a):
+    """a: namespace with cells, genes, perms, resolution, gain, oracle.  Returns the record (a dict)."""
     import torch
     from sctda_b200 import formats, graph, mapper, synth
     X, t, _ = synth.expression_matrix(a.cells, a.genes, seed=synth.SEED)
@@ -63,7 +67,8 @@ def main():
     out['load_s'] = time.perf_counter() - t0
     numpy.random.seed(2017)
     t0 = time.perf_counter()
-    header, rows = c.save(n=a.perms)
+    c.save(n=a.perms)
+    header, rows = c.last_table
     torch.cuda.synchronize()
     out['save_s'] = time.perf_counter() - t0
     out['nodes_lcc'] = len(c.pl)
@@ -106,7 +111,7 @@ def main():
         rel = max(abs(x[5] - y[5]) / abs(y[5]) for x, y in zip(rows, rows2) if y[5] != 0)
         out.update({'table_rows_identical': same_rows, 'p_values_exact': p_exact, 'p_values_tied_genes': p_tied,
                     'p_values_wrong': p_bad, 'max_rel_err_connectivity': rel})
-    print(json.dumps(out))
+    return out
 
 
 if __name__ == '__main__':

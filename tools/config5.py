@@ -78,7 +78,8 @@ def main():
     out['cells_lcc'], out['memberships'] = int(dg.S), int(dg.node_cols.numel())
     perms = synth.permutation_block_torch(a.perms, int(dg.S), seed=7, device=dev).cpu().numpy()
     t0 = time.perf_counter()
-    header, rows = c.save(n=a.perms, perms=perms)
+    c.save(n=a.perms, perms=perms)
+    header, rows = c.last_table
     torch.cuda.synchronize()
     out['save_s'] = time.perf_counter() - t0
     out['rows'] = len(rows)
