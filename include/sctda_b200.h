@@ -317,6 +317,19 @@ int32_t sctda_parse_table_f64(const char* body, int64_t nbytes, int32_t sep, int
                               int64_t ncols, double* out, int64_t* bad_pos, int32_t* bad_len, int64_t bad_cap,
                               int64_t* n_bad, int64_t* bad_row, int32_t nthreads);
 
+/*
+ * HOST function (no GPU work): the numeric fields Preprocess.save writes (ref:663-728), formatted by all
+ * host cores.  counts[nrows][ld] row-major (one row per CELL, ncols genes used); denom[nrows] (the cell's
+ * total transcripts or the subsampling target) or NULL; log2_tpm != 0 writes
+ * str(log2(1.0 + 1000000.0 * count / denom)) as Python 2 prints it ('%.12g', '.0' appended to integral
+ * values), log2_tpm == 0 formats the values as they are.  Row r is written into its own slot
+ * out[r*ncols*25 ...] with `sep` between fields and no line end; row_end[r] = bytes used.  cap must be at
+ * least nrows*ncols*25.  nthreads <= 0: all cores.
+ */
+int32_t sctda_format_table_f64(const double* counts, int64_t ld, int64_t nrows, int64_t ncols,
+                               const double* denom, int32_t log2_tpm, int32_t sep, char* out, int64_t cap,
+                               int64_t* row_end, int32_t nthreads);
+
 /* ---- RootedGraph root finding (first "next" row) ------------------------------- */
 /*
  * RootedGraph.get_dendrite (ref:1463-1479) for all V source nodes at once: hop distances from

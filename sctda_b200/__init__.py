@@ -2,8 +2,8 @@
 
 `import sctda_b200 as scTDA` gives the names of the reference package that lie on the rebuilt path
 (/root/reference/scTDA/__init__.py:1-10): TopologicalRepresentation, UnrootedGraph, RootedGraph,
-benjamini_hochberg.  Preprocess, ParseAyasdiGraph, compare_results and the drawing helpers are out
-of scope.  The names are resolved lazily so that importing the package does not
+benjamini_hochberg, plus write_preprocess_tables (the file formats of Preprocess.save).  The interactive
+Preprocess class, ParseAyasdiGraph, compare_results and the drawing helpers are out of scope.  The names are resolved lazily so that importing the package does not
 load torch or the CUDA library.
 """
 
@@ -14,6 +14,7 @@ _LAZY = {
     'benjamini_hochberg': ('graph', 'benjamini_hochberg'),
     'apply_lens': ('mapper', 'apply_lens'),
     'mapper_graph': ('mapper', 'mapper_graph'),
+    'write_preprocess_tables': ('formats', 'write_preprocess_tables'),
 }
 
 __all__ = sorted(_LAZY)

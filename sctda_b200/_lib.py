@@ -61,6 +61,7 @@ SIGNATURES = {
     'sctda_mt19937_shuffle_rows': (c_i32, [c_ptr, ctypes.POINTER(c_i32), c_i32, c_i32, c_ptr]),
     'sctda_parse_table_f64': (c_i32, [ctypes.c_char_p, c_i64, c_i32, c_i32, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_i64,
                                       ctypes.POINTER(c_i64), ctypes.POINTER(c_i64), c_i32]),
+    'sctda_format_table_f64': (c_i32, [c_ptr, c_i64, c_i64, c_i64, c_ptr, c_i32, c_i32, c_ptr, c_i64, c_ptr, c_i32]),
     'sctda_root_scores': (c_i32, [c_ptr, c_i32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     'sctda_selftest_div': (c_i32, [c_ptr, c_i64, ctypes.POINTER(c_i64)]),
     'sctda_probe_l2_read_gbs': (c_i32, [c_ptr, ctypes.POINTER(c_f64)]),

@@ -14,6 +14,8 @@
 //
 // Output is gene-major, Y[column][row] (the image of `dicgenes`): rows are parsed 32 at a time into
 // a tile and written out transposed, so that every column receives runs of 32 doubles.
+#include <math.h>
+#include <stdio.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -182,3 +184,59 @@ extern "C" int32_t sctda_parse_table_f64(const char* body, int64_t nbytes, int32
     if (*bad_row >= 0) return SCTDA_ERR_INVALID;
     return SCTDA_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Table egress: the numeric fields of Preprocess.save (/root/reference/scTDA/main.py:663-728), i.e.
+// str(numpy.log2(1.0 + 1000000.0 * t / cv)) under Python 2 for every (cell, gene): 12 significant
+// digits ('%.12g'), '.0' appended when the result has neither '.' nor an exponent, 'nan' / 'inf' /
+// '-inf' as Python prints them.  Rows are formatted by all host cores into per-row byte ranges.
+// ------------------------------------------------------------------------------------------------
+static inline int format_py2(double v, char* out) {                    // at most 24 bytes, no terminator needed
+    if (v != v) { memcpy(out, "nan", 3); return 3; }
+    if (v > 1.7976931348623157e308) { memcpy(out, "inf", 3); return 3; }
+    if (v < -1.7976931348623157e308) { memcpy(out, "-inf", 4); return 4; }
+    char buf[40];
+    int n = snprintf(buf, sizeof(buf), "%.12g", v);
+    bool plain = true;
+    for (int i = 0; i < n; ++i)
+        if (buf[i] == '.' || buf[i] == 'e') { plain = false; break; }
+    memcpy(out, buf, (size_t)n);
+    if (plain) { out[n] = '.'; out[n + 1] = '0'; n += 2; }
+    return n;
+}
+
+extern "C" int32_t sctda_format_table_f64(const double* counts, int64_t ld, int64_t nrows, int64_t ncols,
+                                          const double* denom, int32_t log2_tpm, int32_t sep, char* out, int64_t cap,
+                                          int64_t* row_end, int32_t nthreads) {
+    if (!counts || nrows < 0 || ncols < 1 || ld < ncols || !out || !row_end || cap < nrows * ncols * 25) return SCTDA_ERR_INVALID;
+    int nt = nthreads > 0 ? nthreads : (int)std::thread::hardware_concurrency();
+    if (nt < 1) nt = 1;
+    if (nt > 64) nt = 64;
+    if ((int64_t)nt > nrows) nt = (int)(nrows > 0 ? nrows : 1);
+    // every row owns the fixed slot [r * ncols * 25, (r + 1) * ncols * 25) of `out`; row_end[r] = bytes used
+    // (the caller concatenates prefix + slot[:row_end[r]] + '\n'); 24 bytes per value + separator
+    std::atomic<int64_t> next(0);
+    auto work = [&]() {
+        for (;;) {
+            const int64_t r = next.fetch_add(1);
+            if (r >= nrows) break;
+            char* p = out + (size_t)(r * ncols * 25);
+            char* p0 = p;
+            const double* row = counts + (size_t)(r * ld);
+            const double cv = denom ? denom[r] : 1.0;
+            for (int64_t c = 0; c < ncols; ++c) {
+                double v = row[c];
+                if (log2_tpm) v = log2(1.0 + 1000000.0 * v / cv);           // ref:692, 726: the operation order of the reference
+                p += format_py2(v, p);
+                if (c + 1 < ncols) *p++ = (char)sep;
+            }
+            row_end[r] = (int64_t)(p - p0);
+        }
+    };
+    std::vector<std::thread> th;
+    for (int i = 1; i < nt; ++i) th.emplace_back(work);
+    work();
+    for (auto& t : th) t.join();
+    return SCTDA_OK;
+}
+

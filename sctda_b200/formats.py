@@ -230,6 +230,77 @@ def _table_from_native(path, got, shift):
     return [header[c] for c in sel], numpy.ascontiguousarray(Y[sel]), [], [], numpy.zeros(0)
 
 
+def format_rows(values, denom=None, log2_tpm=False, sep='\t', nthreads=0):
+    """The numeric part of table rows as Preprocess.save writes it (ref:686-693): for every row of `values`
+    [rows, cols] the fields str(v) (log2_tpm: str(numpy.log2(1.0 + 1000000.0 * v / denom[row]))) under
+    Python 2's float printing, joined by `sep`.  Formatted by all host cores (sctda_format_table_f64);
+    returns a list of bytes objects, one per row."""
+    import ctypes
+    from . import _lib
+    lib = _lib.load()
+    v = numpy.ascontiguousarray(values, dtype=numpy.float64)
+    rows, cols = v.shape
+    if rows == 0:
+        return []
+    den = None if denom is None else numpy.ascontiguousarray(denom, dtype=numpy.float64)
+    out = numpy.empty(rows * cols * 25, dtype=numpy.uint8)
+    end = numpy.empty(rows, dtype=numpy.int64)
+    rc = lib.sctda_format_table_f64(v.ctypes.data, cols, rows, cols, None if den is None else den.ctypes.data,
+                                    1 if log2_tpm else 0, ord(sep), out.ctypes.data, out.size, end.ctypes.data, int(nthreads))
+    if rc != 0:
+        raise _lib.SctdaError(rc, 'sctda_format_table_f64')
+    slot = cols * 25
+    return [out[r * slot:r * slot + end[r]].tobytes() for r in range(rows)]
+
+
+def write_preprocess_tables(name, genes, counts, long, batch, totaltran=None, which_samples=None, which_genes=None,
+                            counts_subsampled=None, target_subsample=None, block_rows=4096):
+    """Preprocess.save (ref:663-728): writes name.all.tsv and name.mapper.tsv (and name.no_subsampling.tsv
+    when subsampled counts are given) from the state a Preprocess object holds:
+      genes [G] names; counts [G, cells] transcript counts (self.data); long [cells] sampling time points;
+      batch [cells] library ids; totaltran [cells] total transcripts per cell (default: column sums);
+      which_samples [cells] bool mask of the cells to write; which_genes [G] bool mask of the genes of the
+      Mapper table; counts_subsampled / target_subsample: self.data_subsampled / self.target_subsample.
+    Every value is str(numpy.log2(1.0 + 1000000.0 * t / cv)) as Python 2 printed it, cv = total transcripts
+    of the cell, or the subsampling target when subsampled (also for name.no_subsampling.tsv: ref:714-717).
+    The numeric fields are formatted natively by all host cores, block by block of rows."""
+    genes = [str(g) for g in genes]
+    counts = numpy.asarray(counts, dtype=numpy.float64)
+    G, ncell = counts.shape
+    if len(genes) != G:
+        raise ValueError('genes and counts disagree: %d names, %d rows' % (len(genes), G))
+    subsampled = counts_subsampled is not None
+    if subsampled and target_subsample is None:
+        raise ValueError('target_subsample is needed with counts_subsampled')
+    ws = numpy.ones(ncell, dtype=bool) if which_samples is None else numpy.asarray(which_samples, dtype=bool)
+    wg = numpy.ones(G, dtype=bool) if which_genes is None else numpy.asarray(which_genes, dtype=bool)
+    tot = counts.sum(axis=0) if totaltran is None else numpy.asarray(totaltran, dtype=numpy.float64)
+    cells = numpy.nonzero(ws)[0]
+    prefix = [('D' + py2_str(long[n]) + '_' + str(batch[n]) + '_' + str(n) + '\t' + py2_str(long[n]) + '\t' + str(batch[n])
+               + '\t').encode() for n in cells]
+    cv = numpy.full(cells.size, float(target_subsample), dtype=numpy.float64) if subsampled else tot[cells]
+
+    def dump(path, header, data, gene_mask, with_prefix):
+        cols = numpy.nonzero(gene_mask)[0]
+        with open(path, 'wb') as f:
+            f.write(header.encode() + b'\n')
+            for lo in range(0, cells.size, block_rows):
+                sel = cells[lo:lo + block_rows]
+                blockv = numpy.ascontiguousarray(data[numpy.ix_(cols, sel)].T)
+                rows = format_rows(blockv, denom=cv[lo:lo + block_rows], log2_tpm=True)
+                if with_prefix:
+                    f.write(b''.join(prefix[lo + i] + r + b'\n' for i, r in enumerate(rows)))
+                else:
+                    f.write(b''.join(r + b'\n' for r in rows))
+    all_genes = numpy.ones(G, dtype=bool)
+    head_all = 'ID\ttimepoint\tlib\t' + '\t'.join(genes)
+    dump(name + '.all.tsv', head_all, counts_subsampled if subsampled else counts, all_genes, True)
+    if subsampled:
+        dump(name + '.no_subsampling.tsv', head_all, counts, all_genes, True)
+    dump(name + '.mapper.tsv', '\t'.join(g for g, m in zip(genes, wg) if m),
+         counts_subsampled if subsampled else counts, wg, False)
+
+
 def write_genes_tsv(path, header, rows):
     """ref:1063-1067, 1078-1085."""
     with open(path, 'w') as f:

@@ -269,3 +269,67 @@ def test_native_table_parser_fuzz(lib_path, tmp_path):
             assert numpy.array_equal(a[4], b[4], equal_nan=True)
             agreed += 1
     assert agreed > 500
+
+
+def _preprocess_save_reference_rows(genes, counts, long, batch, tot, ws, wg):
+    """ref:663-728 restated with Python-3 formatting helpers (the rows of name.all.tsv / name.mapper.tsv)."""
+    datat = counts.T
+    all_rows, map_rows = ['ID\ttimepoint\tlib\t' + '\t'.join(genes)], ['\t'.join(g for g, m in zip(genes, wg) if m)]
+    for n, m in enumerate(ws):
+        if m:
+            p = 'D' + co.py2_str(long[n]) + '_' + batch[n] + '_' + str(n) + '\t' + co.py2_str(long[n]) + '\t' + batch[n] + '\t'
+            all_rows.append(p + '\t'.join(co.py2_str(numpy.log2(1.0 + 1000000.0 * t / float(tot[n]))) for t in datat[n]))
+            map_rows.append('\t'.join(co.py2_str(numpy.log2(1.0 + 1000000.0 * t / float(tot[n]))) for t in datat[n, wg]))
+    return all_rows, map_rows
+
+
+def test_preprocess_table_writer_round_trip(tmp_path):
+    """formats.write_preprocess_tables (Preprocess.save, ref:663-728): every byte as the reference's loop
+    writes it, and the files read back through read_table / pandas give the values to 12 digits."""
+    from sctda_b200 import formats
+    rng = numpy.random.RandomState(4)
+    G, ncell = 57, 230
+    genes = ['g%d' % i for i in range(G)]
+    counts = rng.poisson(rng.gamma(0.3, 8.0, (G, ncell))).astype(numpy.float64)
+    counts[:, 7] = 0.0
+    counts[3, 7] = 1.0                                           # a cell with one transcript: log2(1 + 1e6) fields
+    long = rng.randint(0, 5, ncell)
+    batch = ['L%d' % (i % 3) for i in range(ncell)]
+    tot = counts.sum(axis=0)
+    ws = rng.rand(ncell) < 0.8
+    ws[7] = True
+    wg = rng.rand(G) < 0.5
+    name = str(tmp_path / 'pp')
+    formats.write_preprocess_tables(name, genes, counts, long, batch, totaltran=tot, which_samples=ws, which_genes=wg,
+                                    block_rows=64)
+    all_rows, map_rows = _preprocess_save_reference_rows(genes, counts, long, batch, tot, ws, wg)
+    with open(name + '.all.tsv') as f:
+        assert f.read() == '\n'.join(all_rows) + '\n'
+    with open(name + '.mapper.tsv') as f:
+        assert f.read() == '\n'.join(map_rows) + '\n'
+    names, Y, cell_id, libs, _ = formats.read_table(name + '.all.tsv', sidecar=False)
+    assert names[3:] == genes and list(libs) == [batch[n] for n in numpy.nonzero(ws)[0]]
+    expect = numpy.log2(1.0 + 1000000.0 * counts[:, ws] / tot[ws][None, :])
+    numpy.testing.assert_allclose(Y[3:], expect, rtol=1e-11, atol=0)
+    # subsampled state: the extra file, the subsampling target as denominator in all three
+    sub = numpy.minimum(counts, 3.0)
+    formats.write_preprocess_tables(name + 's', genes, counts, long, batch, which_samples=ws, which_genes=wg,
+                                    counts_subsampled=sub, target_subsample=500)
+    _, Ys, _, _, _ = formats.read_table(name + 's.all.tsv', sidecar=False)
+    _, Yn, _, _, _ = formats.read_table(name + 's.no_subsampling.tsv', sidecar=False)
+    numpy.testing.assert_allclose(Ys[3:], numpy.log2(1.0 + 1000000.0 * sub[:, ws] / 500.0), rtol=1e-11)
+    numpy.testing.assert_allclose(Yn[3:], numpy.log2(1.0 + 1000000.0 * counts[:, ws] / 500.0), rtol=1e-11)
+
+
+def test_native_formatter_fuzz():
+    """sctda_format_table_f64 against formats.py2_str on every class of value."""
+    from sctda_b200 import formats
+    rng = numpy.random.RandomState(9)
+    v = rng.lognormal(0.0, 12.0, (200, 64)) * rng.choice([-1.0, 1.0], (200, 64))
+    v[rng.rand(200, 64) < 0.3] = 0.0
+    v[0, :8] = [numpy.nan, numpy.inf, -numpy.inf, 1e16, 123456789012.0, -0.0, 0.1 + 0.2, 1e-5]
+    v[1] = numpy.round(v[1])
+    v[2, :4] = [5e-324, 1.7976931348623157e308, 999999999999.5, 99999999999.95]
+    rows = formats.format_rows(v)
+    for r in range(v.shape[0]):
+        assert rows[r].decode() == '\t'.join(formats.py2_str(x) for x in v[r])

@@ -1,5 +1,2 @@
 set -x
-P="python tools/conn_probe.py --genes 2048 --perms 256"
-SCTDA_CONN_LEGACY=1 $P --scores --save gpurun_out/legacy.npz
-$P --order pca --scores --check gpurun_out/legacy.npz
-$P --scores --check gpurun_out/legacy.npz
+python bench.py --steps 3 --warmup 2 --no-mapper --no-cpu > gpurun_out/bench_full.json 2> gpurun_out/bench_full.err; tail -3 gpurun_out/bench_full.err
