@@ -243,6 +243,18 @@ int32_t sctda_pairdist_rows_f64(sctda_ctx* ctx, int32_t N, int32_t G, const doub
 int32_t sctda_smacof_pass(sctda_ctx* ctx, int32_t N, const double* d_D, int64_t ldd, const double* d_Z,
                           double* d_Znew, double* d_stats, void* stream);
 
+/* The PCA lens, apply_lens(df, lens='pca') (ref:745, 753; sklearn.decomposition.PCA(n_components=2)
+ * .fit_transform): d_lens [N, ldl >= 2] receives the two leading principal component scores of the rows of
+ * d_X [N, ldx >= G], with sklearn's sign rule (the loading of largest magnitude of each component is
+ * positive).  Column means, the smaller Gram matrix of the centred table (G x G or N x N, by the FP64
+ * contraction of this library) and its two leading eigenpairs by Chebyshev-filtered block subspace iteration
+ * with Rayleigh-Ritz, stopped when |A q - theta q| <= tol * theta for both (tol <= 0: 1e-12; max_iter <= 0:
+ * 200 outer steps).  d_info [6] (may be NULL): theta_1, theta_2 (squared singular values), the two residuals,
+ * outer steps, status (1 converged, 0 iteration limit).  Synchronises the host every 4 outer steps (reads the
+ * convergence flag). */
+int32_t sctda_pca_lens_f64(sctda_ctx* ctx, int32_t N, int32_t G, const double* d_X, int64_t ldx, double* d_lens,
+                           int64_t ldl, double* d_info, int32_t max_iter, double tol, void* stream);
+
 /* Cover (mapper_graph stage 1).  d_lens [N, ldl>=2]: the 2-D lens.  d_lo0, d_hi0, d_lo1, d_hi1 [r]: open interval
  * bounds per axis (fenceposts widened by gain; the host computes them from percentiles).
  * Patch b = i*r + j holds the cells with lo0[i] < lens0 < hi0[i] and lo1[j] < lens1 < hi1[j].

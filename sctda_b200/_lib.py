@@ -48,6 +48,7 @@ SIGNATURES = {
     'sctda_gram_gather_f64': (c_i32, [c_ptr, c_i32, c_ptr, c_i64, c_i32, c_ptr, c_i32, c_ptr, c_ptr, c_i64, c_ptr]),
     'sctda_pairdist_rows_f64': (c_i32, [c_ptr, c_i32, c_i32, c_ptr, c_i64, c_ptr, c_i32, c_i32, c_i32, c_ptr, c_i64,
                                         c_ptr]),
+    'sctda_pca_lens_f64': (c_i32, [c_ptr, c_i32, c_i32, c_ptr, c_i64, c_ptr, c_i64, c_ptr, c_i32, c_f64, c_ptr]),
     'sctda_smacof_pass': (c_i32, [c_ptr, c_i32, c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_ptr]),
     'sctda_cover_count': (c_i32, [c_ptr, c_i32, c_ptr, c_i64, c_i32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     'sctda_cover_fill': (c_i32, [c_ptr, c_i32, c_i32, c_ptr, c_ptr, c_ptr]),

@@ -366,7 +366,10 @@ extern "C" int32_t sctda_gram_gather_f64(sctda_ctx* ctx, int32_t G, const double
     a.X = d_Xn; a.ldx = ldxn; a.G = G; a.epilogue = EPI_GRAM;
     a.single.rows_a = d_rows_a; a.single.rows_b = d_rows_b; a.single.na = na; a.single.nb = nb;
     a.single.out = d_out; a.single.ldo = ldo;
-    return launch_gemm(ctx, a, cdiv64(na, BM) * cdiv64(nb, BN), (cudaStream_t)stream, ldxn >= ((int64_t)G + 15) / 16 * 16);
+    a.symmetric = (d_rows_a == d_rows_b && na == nb) ? 1 : 0;    // the same rows on both sides: half the tiles, mirrored
+    const int64_t q = cdiv64(nb, BN);
+    return launch_gemm(ctx, a, a.symmetric ? q * (q + 1) / 2 : cdiv64(na, BM) * q, (cudaStream_t)stream,
+                       ldxn >= ((int64_t)G + 15) / 16 * 16);
 }
 
 extern "C" int32_t sctda_pairdist_rows_f64(sctda_ctx* ctx, int32_t N, int32_t G, const double* d_Xn, int64_t ldxn,

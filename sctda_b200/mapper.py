@@ -434,26 +434,25 @@ def apply_lens(df, lens='pca', metric='correlation', dissimilarity=None, device=
     return pandas.DataFrame(out, index=index)
 
 
-def pca_lens_device(Xd):
-    """Two leading principal component scores of the rows of Xd (device), with
-    sklearn.decomposition.PCA's sign rule (largest |loading| of each component positive).
-    Covariance eigen-decomposition through torch (library plumbing, not a hand-written kernel)."""
-    Xc = Xd - Xd.mean(dim=0, keepdim=True)
-    n, g = Xc.shape
-    if g <= n:
-        C = Xc.T @ Xc
-        w, v = torch.linalg.eigh(C)
-        comps = v[:, [-1, -2]].T                                   # [2, G]
-    else:
-        K = Xc @ Xc.T
-        w, u = torch.linalg.eigh(K)
-        u2 = u[:, [-1, -2]]
-        comps = (Xc.T @ u2).T
-        comps = comps / comps.norm(dim=1, keepdim=True)
-    idx = comps.abs().argmax(dim=1)
-    signs = torch.sign(comps[torch.arange(2, device=Xd.device), idx])
-    comps = comps * signs[:, None]
-    return Xc @ comps.T
+def pca_lens_device(Xd, ctx=None, tol=1e-12, max_iter=1000, return_info=False):
+    """Two leading principal component scores of the rows of Xd (device, float64), with
+    sklearn.decomposition.PCA's sign rule (largest |loading| of each component positive):
+    sctda_pca_lens_f64 (csrc/pca.cu: centred Gram matrix by the library's FP64 contraction, two leading
+    eigenpairs by block subspace iteration, no library eigen-solver)."""
+    dev = Xd.device
+    if ctx is None:
+        ctx = _lib.context(dev.index if dev.index is not None else torch.cuda.current_device())
+    Xd = Xd if (Xd.dtype == torch.float64 and Xd.stride(1) == 1) else Xd.to(torch.float64).contiguous()
+    n, g = Xd.shape
+    lens = torch.empty((n, 2), dtype=torch.float64, device=dev)
+    info = torch.zeros(6, dtype=torch.float64, device=dev)
+    ctx.check(ctx.lib.sctda_pca_lens_f64(ctx.handle, int(n), int(g), _lib.ptr(Xd), int(Xd.stride(0)), _lib.ptr(lens), 2,
+                                         _lib.ptr(info), int(max_iter), float(tol), _stream(dev)))
+    if return_info:
+        v = info.cpu().numpy()
+        return lens, {'theta': [float(v[0]), float(v[1])], 'residual': [float(v[2]), float(v[3])],
+                      'iterations': int(v[4]), 'status': int(v[5])}
+    return lens
 
 
 def mapper_graph(df, lens_data, resolution=10, gain=0.5, equalize=True, clust='agglomerative', stat='db', max_K=5,

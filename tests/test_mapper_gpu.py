@@ -410,6 +410,32 @@ def test_distributed_build_equals_single_device_build():
         assert torch.equal(getattr(a, name), getattr(b, name)), name
 
 
+@pytest.mark.parametrize('shape', [(3000, 400), (400, 1500), (1000, 2000), (5000, 64), (257, 257)])
+def test_pca_lens_matches_sklearn(shape):
+    """apply_lens(lens='pca') (ref:745, 753): the device lens (sctda_pca_lens_f64: own Gram contraction + subspace
+    iteration) against sklearn.decomposition.PCA(n_components=2, svd_solver='full').fit_transform, within 1e-7 of
+    the lens scale, for tables with more cells than genes (covariance form) and more genes than cells (dual form)."""
+    import sklearn.decomposition
+    from sctda_b200 import mapper, synth
+    _gpu()
+    n, g = shape
+    X, _, _ = synth.expression_matrix(n, g, seed=n + g)
+    ref = sklearn.decomposition.PCA(n_components=2, svd_solver='full').fit_transform(X)
+    lens, info = mapper.pca_lens_device(torch.from_numpy(X).cuda(), return_info=True)
+    assert info['status'] == 1 and max(info['residual']) <= 1e-12
+    got = lens.cpu().numpy()
+    scale = numpy.abs(ref).max()
+    numpy.testing.assert_allclose(got, ref, rtol=0, atol=1e-7 * scale)
+    # the public seam
+    import pandas
+    df = pandas.DataFrame(X)
+    out = mapper.apply_lens(df, lens='pca')
+    numpy.testing.assert_allclose(out.values, ref, rtol=0, atol=1e-7 * scale)
+    # reproducible bit for bit
+    again = mapper.pca_lens_device(torch.from_numpy(X).cuda()).cpu().numpy()
+    assert (_bits(again) == _bits(got)).all()
+
+
 def test_smacof_matches_sklearn():
     """The device SMACOF (one sctda_smacof_pass per iteration) against sklearn.manifold.smacof from the
     same start: same number of iterations, same stress, same configuration."""
