@@ -262,6 +262,14 @@ def run_case(ref, prefix, n_perm, seed, rooted):
             cen = c.centroid(gi)
             per_gene[str(gi)]['centroid'] = [None if v is None else float(v) for v in cen]
     out['per_gene'] = per_gene
+    # the lib_ / ID_ / _CDR colourings of get_gene and count_gene (ref:902-928, 1347-1383)
+    col = {}
+    for key in ('lib_L1', 'lib_L2', 'ID_' + str(c.cellID[5]), '_CDR'):
+        dic, tol = c.get_gene(key)
+        col[key] = {'tol': float(tol), 'p_nodes': [float(dic[k]) for k in c.pl]}
+    dic, tol = c.count_gene('timepoint', 2.0)
+    col['count timepoint == 2'] = {'tol': float(tol), 'p_nodes': [float(dic[k]) for k in c.pl]}
+    out['colourings'] = col
     # gene x gene matrices over the nodes (ref:1111-1190) on a few genes (the constant, the all-zero
     # and the single-cell gene are left out: their profiles divide by zero in the reference)
     lista = genes[3:11]

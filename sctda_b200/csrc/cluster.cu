@@ -507,33 +507,70 @@ __global__ void __launch_bounds__(kSelThreads) labels_kernel(ClusterArgs a) {
             for (int q = tid; q < m; q += kSelThreads)
                 if (ord[q] >= 0) atomicAdd(&s_cnt[min((int)__ddiv_rn(__dsub_rn(sqrt(w[q]), lo), width), NB - 1)], 1);
         __syncthreads();
+        __shared__ int s_empty;
+        __shared__ int s_scan[kSelThreads];
         if (tid == 0) {
             int empty = -1;
             if (!flat)
                 for (int i = 0; i < NB && empty < 0; ++i)
                     if (s_cnt[i] == 0) empty = i;
-            int32_t* comp = a.labels + off;
-            int32_t* scratch = (int32_t*)(a.TK + (int64_t)off * kMaxK);      // cmin [m], owner [m], rank [m]
-            int32_t* cmin = scratch, *owner = scratch + m, *rank = scratch + 2 * (int64_t)m;
-            int ncomp = 1;
-            comp[0] = 0; cmin[0] = 0;
-            for (int t = 1; t < m; ++t) {
-                const int v = seq[t];
-                bool cut = false;
-                if (empty >= 0) cut = min((int)__ddiv_rn(__dsub_rn(sqrt(w[v]), lo), width), NB - 1) > empty;
-                int c;
-                if (cut) { c = ncomp; cmin[ncomp++] = v; }
-                else { c = comp[par[v]]; if (v < cmin[c]) cmin[c] = v; }
-                comp[v] = c;
-            }
-            for (int v = 0; v < m; ++v) owner[v] = -1;
-            for (int c = 0; c < ncomp; ++c) owner[cmin[c]] = c;
-            int next = 0;
-            for (int v = 0; v < m; ++v)
-                if (owner[v] >= 0) rank[owner[v]] = next++;                      // clusters numbered by smallest member
-            for (int v = 0; v < m; ++v) comp[v] = rank[comp[v]];
-            a.bin_K[b] = ncomp;
+            s_empty = empty;
         }
+        __syncthreads();
+        const int empty = s_empty;
+        // Components of the tree without the cut edges, by the whole CTA: every vertex points at its parent
+        // unless its own edge is cut (the root of its component points at itself); pointer jumping doubles the
+        // distance covered per round; the component's smallest member names it; components are numbered by
+        // smallest member through a prefix count.
+        int32_t* comp = a.labels + off;
+        int32_t* scratch = (int32_t*)(a.TK + (int64_t)off * kMaxK);          // up [m], cmin [m], first [m]
+        int32_t* up = scratch, *cmin = scratch + m, *first = scratch + 2 * (int64_t)m;
+        for (int v = tid; v < m; v += kSelThreads) {
+            bool cut = v == 0 || ord[v] < 0;                                 // vertex 0 is the root of the tree
+            if (!cut && empty >= 0) cut = min((int)__ddiv_rn(__dsub_rn(sqrt(w[v]), lo), width), NB - 1) > empty;
+            up[v] = cut ? v : par[v];
+            cmin[v] = 0x7fffffff;
+            first[v] = 0;
+        }
+        __syncthreads();
+        int32_t* src = up;
+        int32_t* dst = first;                                                // free until the prefix count below
+        for (int span = 1; span < m; span <<= 1) {                           // ceil(log2 m) rounds, ping-pong buffers
+            for (int v = tid; v < m; v += kSelThreads) dst[v] = src[src[v]];
+            __syncthreads();
+            int32_t* t = src; src = dst; dst = t;
+        }
+        if (src != up)
+            for (int v = tid; v < m; v += kSelThreads) up[v] = src[v];
+        __syncthreads();
+        for (int v = tid; v < m; v += kSelThreads) first[v] = 0;
+        __syncthreads();
+        for (int v = tid; v < m; v += kSelThreads) atomicMin(&cmin[up[v]], v);
+        __syncthreads();
+        for (int v = tid; v < m; v += kSelThreads)
+            if (up[v] == v) first[cmin[v]] = 1;                              // v is the smallest member of a component
+        __syncthreads();
+        // exclusive prefix count of `first` over the vertices: contiguous chunks per thread, chunk totals scanned by thread 0
+        const int chunk = (m + kSelThreads - 1) / kSelThreads;
+        const int c0 = min(m, tid * chunk), c1 = min(m, c0 + chunk);
+        int local = 0;
+        for (int v = c0; v < c1; ++v) local += first[v];
+        s_scan[tid] = local;
+        __syncthreads();
+        if (tid == 0) {
+            int run = 0;
+            for (int i = 0; i < kSelThreads; ++i) { const int x = s_scan[i]; s_scan[i] = run; run += x; }
+            a.bin_K[b] = run;
+        }
+        __syncthreads();
+        int run = s_scan[tid];
+        for (int v = c0; v < c1; ++v) {
+            const int f = first[v];
+            first[v] = run;                                                   // number of the component whose smallest member is v
+            run += f;
+        }
+        __syncthreads();
+        for (int v = tid; v < m; v += kSelThreads) comp[v] = first[cmin[up[v]]];
         return;
     }
     // (c) the nlev heaviest tree edges: (weight desc, insertion order desc)

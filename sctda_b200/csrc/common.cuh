@@ -19,7 +19,7 @@ struct sctda_ctx {
     int64_t launches;
     int timing;                          // sctda_set_kernel_timing
     int timed;                           // number of (begin, end) event pairs recorded by the last call
-    cudaEvent_t tev[2 * 16];             // up to 16 launches of the dominant kernel per call
+    cudaEvent_t tev[2 * 64];             // up to 64 launches of the dominant kernel per call
     unsigned attr_done;                  // per-context (= per-device) one-time kernel attribute setup, one bit per file
     cudaStream_t aux_stream;             // second stream for the patch pipeline (cluster.cu)
     cudaEvent_t pipe_ev[4];
@@ -107,5 +107,5 @@ int sctda_conn_perm_tile64(sctda_ctx* ctx, const sctda_graph* gr, int G, const d
 
 // Brackets the dominant kernel of a call with events when timing is on (see sctda_set_kernel_timing).
 #define SCTDA_TIME_RESET(ctx) do { if ((ctx)->timing) (ctx)->timed = 0; } while (0)
-#define SCTDA_TIME_BEGIN(ctx, st) do { if ((ctx)->timing && (ctx)->timed < 16) cudaEventRecord((ctx)->tev[2 * (ctx)->timed], st); } while (0)
-#define SCTDA_TIME_END(ctx, st) do { if ((ctx)->timing && (ctx)->timed < 16) { cudaEventRecord((ctx)->tev[2 * (ctx)->timed + 1], st); (ctx)->timed++; } } while (0)
+#define SCTDA_TIME_BEGIN(ctx, st) do { if ((ctx)->timing && (ctx)->timed < 64) cudaEventRecord((ctx)->tev[2 * (ctx)->timed], st); } while (0)
+#define SCTDA_TIME_END(ctx, st) do { if ((ctx)->timing && (ctx)->timed < 64) { cudaEventRecord((ctx)->tev[2 * (ctx)->timed + 1], st); (ctx)->timed++; } } while (0)

@@ -38,7 +38,7 @@ extern "C" int32_t sctda_ctx_destroy(sctda_ctx* ctx) {
     cudaDeviceSynchronize();
     for (int i = 0; i < SCTDA_NUM_SLOTS; ++i)
         if (ctx->slot_ptr[i]) cudaFree(ctx->slot_ptr[i]);
-    for (int i = 0; i < 32; ++i)
+    for (int i = 0; i < 128; ++i)
         if (ctx->tev[i]) cudaEventDestroy(ctx->tev[i]);
     for (int i = 0; i < 4; ++i)
         if (ctx->pipe_ev[i]) cudaEventDestroy(ctx->pipe_ev[i]);
@@ -75,7 +75,7 @@ extern "C" int32_t sctda_set_kernel_timing(sctda_ctx* ctx, int32_t enabled) {
     if (!ctx) return SCTDA_ERR_INVALID;
     if (enabled && !ctx->tev[0]) {
         SCTDA_CUDA(ctx, cudaSetDevice(ctx->device));
-        for (int i = 0; i < 32; ++i) SCTDA_CUDA(ctx, cudaEventCreate(&ctx->tev[i]));
+        for (int i = 0; i < 128; ++i) SCTDA_CUDA(ctx, cudaEventCreate(&ctx->tev[i]));
     }
     ctx->timing = enabled ? 1 : 0;
     return SCTDA_OK;

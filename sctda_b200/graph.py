@@ -7,6 +7,7 @@ Mirrored: __init__ (ref:785-891), get_gene (ref:893-964), connectivity_pvalue (r
 connectivity (ref:994-1005), delta (ref:1007-1028), expr (ref:1030-1051), save (ref:1053-1086),
 benjamini_hochberg (ref:92-115); RootedGraph.__init__ root/pseudo-time state (ref:1522-1567),
 centroid (ref:1724-1743), save (ref:1879-1914).
+count_gene (ref:1347-1383) and the lib_ / ID_ / _CDR colourings of get_gene (ref:902-928).
 Not mirrored (SURVEY.md §2 "out of scope"): layouts, pickles, drawing, plotting.
 """
 import json
@@ -299,8 +300,13 @@ class UnrootedGraph(object):
     # -- per-gene API (ref:893-1051) ---------------------------------------------------------------
     def get_gene(self, genin, ignore_log=False, con=True):
         """ref:893-964: (dict node -> normalised node value, normalisation factor)."""
-        if genin is not None and not isinstance(genin, list) and (genin[:4] == 'lib_' or genin[:3] == 'ID_' or genin == '_CDR'):
-            raise NotImplementedError('lib_/ID_/_CDR colourings are visualisation helpers (count_gene), out of scope')
+        if genin is not None and not isinstance(genin, list):
+            if 'lib_' in genin[:4]:                                              # ref:902-903
+                return self.count_gene('lib', genin[genin.index('_') + 1:], con=con)
+            if 'ID_' in genin[:3]:                                               # ref:904-905
+                return self.count_gene('ID', genin[genin.index('_') + 1:], con=con)
+            if genin == '_CDR':                                                  # ref:906-928: node means of the cellular detection rate
+                return self._node_means(numpy.asarray(self.cdr, dtype=numpy.float64), con)
         genes = genin if isinstance(genin, list) else [genin]
         dg = self._device_graph(con=con)
         real = genes
@@ -320,6 +326,30 @@ class UnrootedGraph(object):
         if tot > 0.0:
             pol = pol / tot
         return {k: float(v) for k, v in zip(dg.nodes, pol)}, tot
+
+    def _node_means(self, values, con=True):
+        """(dict node -> normalised node mean of a per-cell column, normalisation factor): the tail of
+        get_gene / count_gene (ref:921-928, 1373-1383) for a column given as an array over the table rows;
+        the node means are taken by sctda_node_stats in linear mode."""
+        dg = self._device_graph(con=con)
+        Y = torch.from_numpy(numpy.ascontiguousarray(values, dtype=numpy.float64).reshape(1, -1)).to(dg.device)
+        st = node_stats(self._context(), dg, Y, log2=False, want_p=True)
+        p = st['p'].cpu().numpy()[0]
+        return {k: float(v) for k, v in zip(dg.nodes, p)}, float(st['tol'].cpu().numpy()[0])
+
+    def count_gene(self, genin, cond, con=True):
+        """ref:1347-1383: for every node the fraction of its cells whose column `genin` ('lib', 'ID' or a
+        table column) equals `cond`, normalised to sum 1 over the nodes; returns (dict, normalisation)."""
+        if genin is None:
+            dg = self._device_graph(con=con)
+            return {k: 0.0 for k in dg.nodes}, 0.0
+        if genin == 'lib':
+            geys = numpy.asarray(self.libs, dtype=object)
+        elif genin == 'ID':
+            geys = numpy.asarray(self.cellID, dtype=object)
+        else:
+            geys = self.Y[self.gene_row[genin]]
+        return self._node_means((geys == cond).astype(numpy.float64), con)
 
     def connectivity(self, genis, ind=1):
         """ref:994-1005."""

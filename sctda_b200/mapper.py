@@ -511,9 +511,11 @@ class TopologicalRepresentation(object):
         else:
             self.lens_data_mds = apply_lens(self.df, lens=lens, device=device, **kwargs)
 
-    def save(self, name, resolution, gain, equalize=True, cluster='agglomerative', statistics='db', max_K=5,
+    def save(self, name, resolution, gain, equalize=True, cluster='agglomerative', statistics='db', max_K=5, *,
              cluster_metric='euclidean', precision='fp64'):
-        """ref:758-778: writes name.json and name.gexf, returns the patches."""
+        """ref:758-778: writes name.json and name.gexf, returns the patches.  The positional signature is
+        the reference's; `cluster_metric` and `precision` are keyword-only extensions (the opt-in
+        contraction precision of include/sctda_b200.h)."""
         G, all_clusters, patches = mapper_graph(self.df, lens_data=self.lens_data_mds, resolution=resolution, gain=gain,
                                                 equalize=equalize, clust=cluster, stat=statistics, max_K=max_K,
                                                 metric=cluster_metric, device=self.device, precision=precision)

@@ -159,6 +159,11 @@ def test_golden_reference_vectors(golden_dir, tmp_path, name):
                 assert cen == [None, None]
             else:
                 numpy.testing.assert_allclose(cen, r['centroid'], rtol=1e-10)
+    # the lib_ / ID_ / _CDR colourings and count_gene (ref:902-928, 1347-1383) against the reference's own values
+    for key, r in ref['colourings'].items():
+        dic, tol = c.count_gene('timepoint', 2.0) if key.startswith('count ') else c.get_gene(key)
+        assert tol == pytest.approx(r['tol'], rel=1e-12, abs=0)
+        numpy.testing.assert_allclose([dic[k] for k in c.pl], numpy.array(r['p_nodes'])[order], rtol=1e-12, atol=0)
     # the table writer, RNG stream consumed gene by gene from `seed` (ref:1068-1071)
     genes = sorted(c.gene_row.keys())
     numpy.random.seed(ref['seed'])
