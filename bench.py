@@ -71,7 +71,7 @@ def workload_config(a, n_gpus):
                         % (a.nodes, a.genes, a.perms, a.cells, n_gpus),
             'nodes': a.nodes, 'cells': a.cells, 'genes': a.genes, 'perms': a.perms,
             'permutations': 'one shared [n,S] int32 block (input)', 'l2': 'inputs_exceed_l2',
-            'final_gather': 'counts of all ranks gathered on rank 0 inside the timed region',
+            'final_gather': 'counts of all ranks gathered inside the timed region (sctda_gather_results: ncclAllGather on device buffers)',
             'parallelism': 'genes/%d' % n_gpus}
 
 
@@ -440,7 +440,7 @@ def run_own(a):
     ctx.set_kernel_timing(True)
 
     # ---- inputs, resident in HBM before the timed region ----
-    from sctda_b200 import geneorder
+    from sctda_b200 import geneorder, parallel
     members, adj, _ = synth.connectivity_case(a.cells, a.nodes, 1, seed=synth.SEED)
     dg = graph.DeviceGraph(members, adj, numpy.arange(a.cells), a.cells, local)
     g_lo = (a.genes * rank) // world
@@ -471,14 +471,7 @@ def run_own(a):
         """One pass of the test over this rank's gene shard, then the final gather ("... to
         exceed counts for all genes on device 0"): the only collective of the path."""
         ex, ties, _ = graph.conn_perm_test(ctx, dg, Y, perms, observed, log2=True, gene_order=order)
-        if world > 1:
-            pad = torch.zeros(Gmax, dtype=torch.int32, device=dev)
-            pad[:G] = ex
-            buf = torch.empty(world * Gmax, dtype=torch.int32, device=dev) if rank == 0 else None
-            dist.gather(pad, list(buf.view(world, Gmax).unbind(0)) if rank == 0 else None, dst=0)
-            gathered[0] = buf
-        else:
-            gathered[0] = ex
+        gathered[0] = parallel.gather_counts_device(ctx, ex, Gmax)       # sctda_gather_results (NCCL on device buffers)
         return ex, ties
 
     for _ in range(a.warmup):
@@ -517,13 +510,8 @@ def run_own(a):
 
         def e2e_step():
             counts = graph.conn_perm_test_host(ctx, dg, Yh, Ph, Oh, log2=True)
-            if world > 1:                                          # the per-rank counts meet on rank 0 (host)
-                pad = torch.zeros(Gmax, dtype=torch.int32, device=dev)
-                pad[:G] = counts.to(dev)
-                buf = torch.empty(world * Gmax, dtype=torch.int32, device=dev) if rank == 0 else None
-                dist.gather(pad, list(buf.view(world, Gmax).unbind(0)) if rank == 0 else None, dst=0)
-                if rank == 0:
-                    counts = buf.cpu()
+            if world > 1:                                          # the per-rank counts meet on every rank, then the host
+                counts = parallel.gather_counts_device(ctx, counts.to(dev), Gmax).cpu()
             return counts
         e2e_step()                                                 # warm-up (allocations)
         barrier()

@@ -294,6 +294,32 @@ int32_t sctda_nerve_count(sctda_ctx* ctx, int32_t N, int32_t V, const int32_t* d
                           const int32_t* d_node_members, int64_t Mtot, int64_t* d_edge_count, void* stream);
 int32_t sctda_nerve_fill(sctda_ctx* ctx, int32_t V, int32_t* d_edges, void* stream);
 
+/* ---- multi-GPU glue: one process per GPU, communicator created by the host -------- */
+/*
+ * nccl_comm is an ncclComm_t (passed as void*) the HOST created with ncclCommInitRank, one rank per GPU; this
+ * library never initialises NCCL and resolves ncclAllGather at run time from the libnccl.so.2 loaded in the
+ * process.  All buffers are device buffers; nothing synchronises the host.
+ *
+ * sctda_csr_select: the sub-CSR of the patches d_sel [nsel] (ascending patch ids) of the cover CSR:
+ *   d_sub_members[d_sub_off[i] + t] = d_members[d_bin_off[d_sel[i]] + t]  (d_sub_off [nsel+1] given by the caller).
+ * sctda_allgather_csr: the ONE exchange of the patch-sharded Mapper build.  This rank clustered its patches
+ *   (sctda_bin_cluster on its sub-CSR): d_frag_labels [frag_len], d_frag_K [frag_nb].  Fragments are padded to
+ *   max_frag / max_nb (the maxima over the ranks), all-gathered, and every patch b of the full cover is placed:
+ *   d_labels[d_bin_off[b] + t] = fragment of rank d_owner[b] at d_frag_off[b] + t, d_bin_K[b] = its K at d_frag_idx[b].
+ *   With nranks == 1 the communicator may be NULL (the gather is a local copy).
+ * sctda_gather_results: the final gather of the permutation test (no other collective on that path):
+ *   d_all [nranks * max_n] receives every rank's d_mine [n_mine], padded to max_n, in rank order.
+ */
+int32_t sctda_csr_select(sctda_ctx* ctx, int32_t nsel, const int32_t* d_sel, const int32_t* d_bin_off,
+                         const int32_t* d_members, const int32_t* d_sub_off, int32_t* d_sub_members, void* stream);
+int32_t sctda_allgather_csr(sctda_ctx* ctx, void* nccl_comm, int32_t nranks, const int32_t* d_frag_labels,
+                            int64_t frag_len, int64_t max_frag, const int32_t* d_frag_K, int32_t frag_nb,
+                            int32_t max_nb, int32_t nbins, const int32_t* d_bin_off, const int32_t* d_owner,
+                            const int32_t* d_frag_off, const int32_t* d_frag_idx, int32_t* d_labels,
+                            int32_t* d_bin_K, void* stream);
+int32_t sctda_gather_results(sctda_ctx* ctx, void* nccl_comm, int32_t nranks, const int32_t* d_mine,
+                             int64_t n_mine, int64_t max_n, int32_t* d_all, void* stream);
+
 /* ---- gene x gene matrices over the nodes ---------------------------------- */
 /*
  * UnrootedGraph.JSD_matrix (ref:1111-1155): Jensen-Shannon distance between the normalised node

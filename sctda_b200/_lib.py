@@ -58,6 +58,10 @@ SIGNATURES = {
     'sctda_nodes_fill': (c_i32, [c_ptr, c_i32, c_ptr, c_ptr, c_ptr, c_ptr, c_i32, c_ptr, c_ptr, c_ptr, c_ptr]),
     'sctda_nerve_count': (c_i32, [c_ptr, c_i32, c_i32, c_ptr, c_ptr, c_i64, c_ptr, c_ptr]),
     'sctda_nerve_fill': (c_i32, [c_ptr, c_i32, c_ptr, c_ptr]),
+    'sctda_csr_select': (c_i32, [c_ptr, c_i32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
+    'sctda_allgather_csr': (c_i32, [c_ptr, c_ptr, c_i32, c_ptr, c_i64, c_i64, c_ptr, c_i32, c_i32, c_i32, c_ptr, c_ptr, c_ptr,
+                                    c_ptr, c_ptr, c_ptr, c_ptr]),
+    'sctda_gather_results': (c_i32, [c_ptr, c_ptr, c_i32, c_ptr, c_i64, c_i64, c_ptr, c_ptr]),
     'sctda_jsd_matrix': (c_i32, [c_ptr, c_i32, c_i32, c_ptr, c_i64, c_ptr, c_i64, c_ptr]),
     'sctda_mt19937_shuffle_rows': (c_i32, [c_ptr, ctypes.POINTER(c_i32), c_i32, c_i32, c_ptr]),
     'sctda_parse_table_f64': (c_i32, [ctypes.c_char_p, c_i64, c_i32, c_i32, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_i64,

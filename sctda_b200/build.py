@@ -60,7 +60,7 @@ def build(force=False, verbose=False):
         if verbose:
             sys.stderr.write(out)
     if force or procs or _stale(LIB, objs):
-        cmd = [nvcc, '-shared', '-o', LIB] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a']
+        cmd = [nvcc, '-shared', '-o', LIB] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a', '-ldl']
         r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
         if r.returncode != 0:
             raise RuntimeError('link failed: %s\n%s' % (' '.join(cmd), r.stdout.decode()))

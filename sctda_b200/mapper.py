@@ -307,12 +307,20 @@ def cluster_sub_csr(ctx, Xn, sub_off, sub_members, max_K=5):
     return labels[:m].cpu().numpy(), K[:nb].cpu().numpy()
 
 
-def build_graph_distributed(ctx, Xd, lens, resolution, gain, equalize=True, max_K=5, metric='euclidean', profile=None):
+def build_graph_distributed(ctx, Xd, lens, resolution, gain, equalize=True, max_K=5, metric='euclidean', profile=None,
+                            exchange='device'):
     """The graph build with the per-patch clustering sharded over the ranks of the default
     process group: X and the lens are replicated, patches are dealt by
-    descending m^2, labels are exchanged by one all_gather, cover / nodes / nerve are replicated.
-    Returns the same MapperDeviceResult on every rank."""
+    descending m^2, cover / nodes / nerve are replicated.  Returns the same MapperDeviceResult on every rank.
+
+    exchange='device' (default on GPUs): only the patch sizes (a few KB) visit the host, to plan the shards; the
+    sub-CSR of this rank's patches is cut on the device (sctda_csr_select), and the label fragments meet
+    through ONE pair of ncclAllGather calls on device buffers followed by a placement kernel
+    (sctda_allgather_csr, communicator from parallel.nccl_comm).
+    exchange='host': the round-1 path through host arrays and torch.distributed.all_gather
+    (parallel.patch_sharded_labels); kept for the gloo tests of the host logic."""
     from . import parallel
+    import time as _time
     dev = Xd.device
     N, G = Xd.shape
     r = int(resolution)
@@ -331,33 +339,63 @@ def build_graph_distributed(ctx, Xd, lens, resolution, gain, equalize=True, max_
     res.bin_off = torch.empty(B + 1, dtype=torch.int32, device=dev)
     ctx.check(ctx.lib.sctda_cover_count(ctx.handle, N, _lib.ptr(lens_d), 2, r, _lib.ptr(b[0]), _lib.ptr(b[1]),
                                         _lib.ptr(b[2]), _lib.ptr(b[3]), _lib.ptr(res.bin_off), st))
-    import time as _time
-    bin_off = res.bin_off.cpu().numpy()
+    bin_off = res.bin_off.cpu().numpy()                       # B + 1 integers: the plan needs the patch sizes
     _t = [_time.perf_counter()]
     mtot = int(bin_off[B])
     _b_members = _Buf(mtot, torch.int32, dev)
     res.members = _b_members.view
     ctx.check(ctx.lib.sctda_cover_fill(ctx.handle, N, r, _lib.ptr(res.bin_off), _b_members.ptr, st))
-    members_h = res.members.cpu().numpy()
-    _t.append(_time.perf_counter())
-
-    def _compute(so, sm):
-        out = cluster_sub_csr(ctx, Xn, so, sm, max_K)
+    if exchange == 'host':
+        members_h = res.members.cpu().numpy()
         _t.append(_time.perf_counter())
-        return out
-    labels, bin_K = parallel.patch_sharded_labels(bin_off, members_h, _compute)
-    _t.append(_time.perf_counter())
-    res.labels = torch.as_tensor(labels).to(dev)
-    res.bin_K = torch.as_tensor(bin_K).to(dev)
+
+        def _compute(so, sm):
+            out = cluster_sub_csr(ctx, Xn, so, sm, max_K)
+            _t.append(_time.perf_counter())
+            return out
+        labels, bin_K = parallel.patch_sharded_labels(bin_off, members_h, _compute)
+        _t.append(_time.perf_counter())
+        res.labels = torch.as_tensor(labels).to(dev)
+        res.bin_K = torch.as_tensor(bin_K).to(dev)
+    else:
+        rank, ws = parallel.world()
+        sizes = bin_off[1:].astype(numpy.int64) - bin_off[:-1]
+        plan = parallel.patch_shard_plan(sizes, rank, ws)
+        nb = int(plan['mine'].size)
+        frag_len = int(plan['sub_off'][-1])
+        small = numpy.concatenate([plan['mine'], plan['sub_off'], plan['owner'], plan['frag_off'], plan['frag_idx']])
+        small_d = torch.from_numpy(small.astype(numpy.int32)).to(dev, non_blocking=True)      # one small upload
+        o = numpy.cumsum([0, nb, nb + 1, B, B, B])
+        mine_d, sub_off_d, owner_d, frag_off_d, frag_idx_d = [small_d[o[i]:o[i + 1]] for i in range(5)]
+        _t.append(_time.perf_counter())
+        sub_members = _Buf(frag_len, torch.int32, dev)
+        ctx.check(ctx.lib.sctda_csr_select(ctx.handle, nb, _nonnull(mine_d), _lib.ptr(res.bin_off), _b_members.ptr,
+                                           _nonnull(sub_off_d), sub_members.ptr, st))
+        frag_labels = _Buf(frag_len, torch.int32, dev)
+        frag_K = _Buf(nb, torch.int32, dev)
+        if nb:
+            ctx.check(ctx.lib.sctda_bin_cluster(ctx.handle, G, _lib.ptr(Xn), int(Xn.stride(0)), nb, _nonnull(sub_off_d),
+                                                sub_members.ptr, int(max_K), 0, frag_labels.ptr, frag_K.ptr, None, st))
+        _t.append(_time.perf_counter())
+        _b_labels = _Buf(mtot, torch.int32, dev)
+        res.labels = _b_labels.view
+        res.bin_K = torch.empty(B, dtype=torch.int32, device=dev)
+        comm = parallel.nccl_comm(dev.index) if ws > 1 else None
+        ctx.check(ctx.lib.sctda_allgather_csr(ctx.handle, comm, ws, frag_labels.ptr, frag_len, int(plan['max_frag']),
+                                              frag_K.ptr, nb, int(plan['max_nb']), B, _lib.ptr(res.bin_off),
+                                              _lib.ptr(owner_d), _lib.ptr(frag_off_d), _lib.ptr(frag_idx_d),
+                                              _b_labels.ptr, _lib.ptr(res.bin_K), st))
+        _t.append(_time.perf_counter())
     res.bin_db = None
     _finish_nodes_and_nerve(ctx, res, N, mtot)
     if profile is not None:
         e1.record(torch.cuda.current_stream(dev))
         torch.cuda.current_stream(dev).synchronize()
         _t.append(_time.perf_counter())
-        profile.update({'host_ms': {'cover_to_host': 1e3 * (_t[1] - _t[0]), 'cluster_shard': 1e3 * (_t[2] - _t[1]),
+        profile.update({'host_ms': {'plan_and_upload' if exchange != 'host' else 'cover_to_host': 1e3 * (_t[1] - _t[0]),
+                                    'cluster_shard': 1e3 * (_t[2] - _t[1]),
                                     'exchange_and_merge': 1e3 * (_t[3] - _t[2]), 'nodes_nerve': 1e3 * (_t[4] - _t[3])},
-                        'total_ms': e0.elapsed_time(e1), 'Mtot': mtot, 'V': res.V, 'E': res.E,
+                        'exchange': exchange, 'total_ms': e0.elapsed_time(e1), 'Mtot': mtot, 'V': res.V, 'E': res.E,
                         'gemm_ms': ctx.last_kernel_ms() if ctx.timing_enabled else None})
     return res
 

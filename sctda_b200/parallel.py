@@ -115,3 +115,88 @@ def patch_sharded_labels(bin_off, members, compute):
             bin_K[b] = kr[i]
             pos += m
     return labels, bin_K
+
+
+# ----------------------------------------------------------------------------------------------
+# NCCL communicator for the library's own collectives (include/sctda_b200.h: sctda_allgather_csr,
+# sctda_gather_results): created HERE, by the host, with ctypes on the process's libnccl.so.2;
+# torch.distributed only carries the 128-byte unique id from rank 0 to the others.
+# ----------------------------------------------------------------------------------------------
+_nccl_comm = {}
+
+
+def nccl_comm(device):
+    """The ncclComm_t (as ctypes.c_void_p) of this rank for the default process group, created once per
+    process.  Needs an initialised torch.distributed group (any backend) and one GPU per rank."""
+    import ctypes
+    if 'comm' in _nccl_comm:
+        return _nccl_comm['comm']
+    rank, ws = world()
+
+    class UniqueId(ctypes.Structure):
+        _fields_ = [('internal', ctypes.c_char * 128)]
+    lib = ctypes.CDLL('libnccl.so.2', mode=ctypes.RTLD_GLOBAL)          # the copy torch has already loaded
+    lib.ncclGetUniqueId.argtypes = [ctypes.POINTER(UniqueId)]
+    lib.ncclCommInitRank.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, UniqueId, ctypes.c_int]
+    uid = UniqueId()
+    if rank == 0:
+        rc = lib.ncclGetUniqueId(ctypes.byref(uid))
+        if rc != 0:
+            raise RuntimeError('ncclGetUniqueId failed (%d)' % rc)
+    cdev = _comm_device()
+    t = torch.frombuffer(bytearray(bytes(uid)), dtype=torch.uint8).clone().to(cdev)
+    dist.broadcast(t, src=0)
+    ctypes.memmove(ctypes.byref(uid), bytes(t.cpu().numpy().tobytes()), 128)
+    torch.cuda.set_device(device)
+    comm = ctypes.c_void_p()
+    rc = lib.ncclCommInitRank(ctypes.byref(comm), int(ws), uid, int(rank))
+    if rc != 0:
+        raise RuntimeError('ncclCommInitRank failed (%d)' % rc)
+    _nccl_comm['comm'] = comm
+    _nccl_comm['lib'] = lib
+    return comm
+
+
+def patch_shard_plan(sizes, rank, world_size):
+    """Host plan of the patch-sharded build from the patch sizes [B] alone (a few KB): patches dealt by
+    descending m^2 (assign_patches_lpt).  Returns a dict of small int32 arrays:
+      mine [nb]       ascending patch ids of this rank,   sub_off [nb+1]  CSR offsets of its sub-CSR,
+      owner [B]       rank that clusters each patch,      frag_off [B]    offset of the patch inside its owner's
+      frag_idx [B]    index of the patch among its owner's patches,        label fragment,
+      max_frag, max_nb  the largest fragment / patch count over the ranks."""
+    sizes = numpy.asarray(sizes, dtype=numpy.int64)
+    parts = assign_patches_lpt(sizes, world_size)
+    B = sizes.size
+    owner = numpy.zeros(B, dtype=numpy.int32)
+    frag_off = numpy.zeros(B, dtype=numpy.int32)
+    frag_idx = numpy.zeros(B, dtype=numpy.int32)
+    max_frag, max_nb = 0, 0
+    for r, p in enumerate(parts):
+        owner[p] = r
+        off = numpy.zeros(p.size + 1, dtype=numpy.int64)
+        numpy.cumsum(sizes[p], out=off[1:])
+        frag_off[p] = off[:-1]
+        frag_idx[p] = numpy.arange(p.size)
+        max_frag = max(max_frag, int(off[-1]))
+        max_nb = max(max_nb, int(p.size))
+        if r == rank:
+            mine, sub_off = p.astype(numpy.int32), off.astype(numpy.int32)
+    return {'mine': mine, 'sub_off': sub_off, 'owner': owner, 'frag_off': frag_off, 'frag_idx': frag_idx,
+            'max_frag': max_frag, 'max_nb': max_nb}
+
+
+def gather_counts_device(ctx, mine, max_n):
+    """The final gather of the permutation test on device buffers (sctda_gather_results, NCCL): `mine` int32
+    device tensor of this rank's per-gene counts, max_n the largest shard.  Returns the [world, max_n] int32
+    device tensor (rank-major, shards padded with zeros) on every rank; one rank: `mine` itself."""
+    import ctypes
+    from . import _lib
+    rank, ws = world()
+    if ws == 1:
+        return mine
+    dev = mine.device
+    out = torch.empty((ws, int(max_n)), dtype=torch.int32, device=dev)
+    ctx.check(ctx.lib.sctda_gather_results(ctx.handle, nccl_comm(dev.index), ws, _lib.ptr(mine), int(mine.numel()), int(max_n),
+                                           _lib.ptr(out), ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+    return out
+

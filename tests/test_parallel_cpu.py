@@ -121,3 +121,40 @@ def test_lpt_assignment_and_shards():
     assert so.tolist() == [0, 2, 5] and sm.tolist() == [9, 8, 7, 6, 5]
     so, sm = parallel.sub_csr(off, numpy.array([9, 8, 7, 6, 5]), numpy.array([1]))
     assert so.tolist() == [0, 0] and sm.tolist() == []
+
+
+@pytest.mark.parametrize('ws', [1, 2, 3, 8])
+def test_patch_shard_plan_places_every_fragment(ws):
+    """parallel.patch_shard_plan (the host plan of the device-side exchange, sctda_allgather_csr): emulating
+    every rank's label fragment and the placement kernel in numpy reassembles the full label array, for
+    ragged and empty patches; fragments never exceed max_frag / max_nb."""
+    from sctda_b200 import parallel
+    rng = numpy.random.RandomState(ws)
+    sizes = rng.randint(0, 40, 57)
+    sizes[[3, 9]] = 0
+    sizes[5] = 400
+    bin_off = numpy.concatenate([[0], numpy.cumsum(sizes)])
+    truth = rng.randint(0, 5, int(bin_off[-1])).astype(numpy.int32)
+    truth_K = rng.randint(0, 6, sizes.size).astype(numpy.int32)
+    plans = [parallel.patch_shard_plan(sizes, r, ws) for r in range(ws)]
+    max_frag, max_nb = plans[0]['max_frag'], plans[0]['max_nb']
+    gathered = numpy.zeros((ws, max(max_frag, 1)), dtype=numpy.int32)
+    gathered_K = numpy.zeros((ws, max(max_nb, 1)), dtype=numpy.int32)
+    seen = numpy.zeros(sizes.size, dtype=int)
+    for r, p in enumerate(plans):
+        assert (p['owner'] == plans[0]['owner']).all() and p['max_frag'] == max_frag and p['max_nb'] == max_nb
+        assert p['sub_off'][-1] <= max_frag and p['mine'].size <= max_nb
+        assert (numpy.diff(p['mine']) > 0).all()
+        for i, b in enumerate(p['mine']):                          # the rank's sub-CSR and its fragment
+            assert p['owner'][b] == r and p['frag_idx'][b] == i and p['frag_off'][b] == p['sub_off'][i]
+            gathered[r, p['sub_off'][i]:p['sub_off'][i + 1]] = truth[bin_off[b]:bin_off[b + 1]]
+            gathered_K[r, i] = truth_K[b]
+            seen[b] += 1
+    assert (seen == 1).all()
+    owner, frag_off, frag_idx = plans[0]['owner'], plans[0]['frag_off'], plans[0]['frag_idx']
+    labels = numpy.empty_like(truth)
+    K = numpy.empty_like(truth_K)
+    for b in range(sizes.size):                                    # place_fragments_kernel
+        labels[bin_off[b]:bin_off[b + 1]] = gathered[owner[b], frag_off[b]:frag_off[b] + sizes[b]]
+        K[b] = gathered_K[owner[b], frag_idx[b]]
+    assert (labels == truth).all() and (K == truth_K).all()
