@@ -31,7 +31,8 @@
 int sctda_internal_gram_bins(sctda_ctx* ctx, int G, const double* d_Xn, int64_t ldxn, int nprob,
                              const int32_t* d_prob_bin, const int32_t* d_bin_off, const int32_t* d_members,
                              const int64_t* d_tile_prefix, const int64_t* d_gram_off, double* d_gram, cudaStream_t st,
-                             int64_t nrows, bool reuse_split);
+                             int64_t nrows, bool reuse_split, int prob_begin, int prob_end, unsigned long long* d_tile_counter,
+                             int grid_ctas, bool untimed, int tiles_per_cta);
 
 namespace {
 
@@ -1083,7 +1084,9 @@ extern "C" int32_t sctda_bin_cluster(sctda_ctx* ctx, int32_t G, const double* d_
         }
     }
     if (!ctx->fork_stream) {
-        SCTDA_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->fork_stream, cudaStreamNonBlocking));
+        int prio_lo = 0, prio_hi = 0;                 // the highest priority: when the Gram tiles of the large patches are
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);      // done, their MST kernels must win the freed SMs over the next contraction
+        SCTDA_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->fork_stream, cudaStreamNonBlocking, prio_hi));
         for (int i = 0; i < 2; ++i) SCTDA_CUDA(ctx, cudaEventCreateWithFlags(&ctx->fork_ev[i], cudaEventDisableTiming));
     }
     if (!ctx->aux_stream) {
@@ -1149,14 +1152,7 @@ extern "C" int32_t sctda_bin_cluster(sctda_ctx* ctx, int32_t G, const double* d_
         SCTDA_CUDA(ctx, cudaMemcpyAsync(d_chunks, bt.chunks.data(), (size_t)(nb + 1) * 8, cudaMemcpyHostToDevice, st));
         SCTDA_CUDA(ctx, cudaMemcpyAsync(d_prob, order.data() + bt.pos, (size_t)nb * 4, cudaMemcpyHostToDevice, st));
         a.prob_bin = d_prob; a.gram_off = d_goff; a.gram = gram_buf[k];
-        int rc = sctda_internal_gram_bins(ctx, G, d_Xn, ldxn, nb, d_prob, d_bin_off, d_members, d_tiles, d_goff, gram_buf[k], st,
-                                          x_rows, i > 0);
-        if (rc) return rc;
-        if (pipe) {
-            SCTDA_CUDA(ctx, cudaEventRecord(ctx->pipe_ev[k], st));
-            SCTDA_CUDA(ctx, cudaStreamWaitEvent(aux_st, ctx->pipe_ev[k], 0));
-        }
-        // MST: patches are sorted by size; [0,n_huge) above 28,000 cells (generic kernel, state in
+        // MST size classes: patches are sorted by size; [0,n_huge) above 28,000 cells (generic kernel, state in
         // global memory), [n_huge,n_big) above 16,384 and [n_big,n_mid) above 4,096 (one cluster of 8
         // CTAs per patch, 8 or 4 register keys per thread), the rest one CTA with 8 register keys
         int n_huge = 0, n_big = 0, n_mid = 0, n_1k = 0, n_512 = 0;
@@ -1168,31 +1164,71 @@ extern "C" int32_t sctda_bin_cluster(sctda_ctx* ctx, int32_t G, const double* d_
             if (m > thr_1k) ++n_1k;
             if (m > thr_512) ++n_512;
         }
-        // The cluster launches (few SMs, long dependent chains) and the one-CTA launch (all other patches)
-        // run side by side: fork the latter onto a second stream, join before the selection kernels.
+        // The dependent chain of a large patch's MST (tens of ms on 8 SMs) is hidden behind the contraction of
+        // the other patches: the Gram tiles of the large patches are computed first, their cluster MST kernels
+        // start on a second stream as soon as those tiles exist, and the contraction of the remaining patches
+        // runs beside them on the other SMs (tiles claimed from a counter, so that CTAs which only find a free
+        // SM when an MST kernel ends do not hold work back).
+        // MEASURED on a rank's share of the 8-GPU 100k x 2k build (tools/mapper_rank.py, B200): 148.3 -> 148.0 ms and
+        // 139.5 -> 137.4 ms.  The MST chain does disappear behind the contraction, but the contraction pays it back:
+        // 111 -> 132 ms as short-lived CTAs sharing the SMs and the L2 with the MST kernels (a persistent launch on
+        // the SMs left over, plus a helper launch afterwards, did no better: 152 ms).  Opt-in (SCTDA_OVERLAP=1).
+        static const bool want_overlap = getenv("SCTDA_OVERLAP") && atoi(getenv("SCTDA_OVERLAP")) != 0;
+        const bool overlap = want_overlap && !pipe && ctx->precision == 0 && n_mid > 0 && nb > n_mid;
+        int rc;
+        if (overlap) {
+            unsigned long long* ctr = (unsigned long long*)sctda_ws(ctx, WS_MISC2, 256);
+            if (!ctr) return SCTDA_ERR_NOMEM;
+            SCTDA_CUDA(ctx, cudaMemsetAsync(ctr, 0, 2 * sizeof(unsigned long long), st));
+            rc = sctda_internal_gram_bins(ctx, G, d_Xn, ldxn, nb, d_prob, d_bin_off, d_members, d_tiles, d_goff, gram_buf[k], st,
+                                          x_rows, i > 0, 0, n_mid, ctr, 0, false, 0);
+            if (rc) return rc;
+            SCTDA_CUDA(ctx, cudaEventRecord(ctx->fork_ev[0], st));
+            SCTDA_CUDA(ctx, cudaStreamWaitEvent(ctx->fork_stream, ctx->fork_ev[0], 0));
+            // The contraction of the remaining patches runs as short-lived CTAs (eight tiles each, claimed from the
+            // counter): SMs turn over every ~150 us, so the MST clusters of the higher-priority stream get theirs as
+            // soon as the large patches' tiles exist, and the contraction takes them back when an MST kernel ends.
+            const int64_t tiles2 = bt.tiles[nb] - bt.tiles[n_mid];
+            rc = sctda_internal_gram_bins(ctx, G, d_Xn, ldxn, nb, d_prob, d_bin_off, d_members, d_tiles, d_goff, gram_buf[k], st,
+                                          x_rows, true, n_mid, nb, ctr + 1, (int)std::max<int64_t>(1, (tiles2 + 7) / 8), false, 8);
+            if (rc) return rc;
+        } else {
+            rc = sctda_internal_gram_bins(ctx, G, d_Xn, ldxn, nb, d_prob, d_bin_off, d_members, d_tiles, d_goff, gram_buf[k], st,
+                                          x_rows, i > 0, 0, 0, nullptr, 0, false, 0);
+            if (rc) return rc;
+        }
+        if (pipe) {
+            SCTDA_CUDA(ctx, cudaEventRecord(ctx->pipe_ev[k], st));
+            SCTDA_CUDA(ctx, cudaStreamWaitEvent(aux_st, ctx->pipe_ev[k], 0));
+        }
+        // Without the overlap: the cluster launches (few SMs, long dependent chains) and the one-CTA launch (all
+        // other patches) still run side by side: the latter is forked onto the second stream, joined before the
+        // selection kernels.  With it the roles are swapped: the cluster launches are the ones on the second stream.
         static const bool no_fork = getenv("SCTDA_NO_FORK") && atoi(getenv("SCTDA_NO_FORK")) != 0;
-        const bool fork = !no_fork && n_mid > 0 && nb > n_mid;
-        cudaStream_t reg_st = aux_st;
-        if (fork) {
+        const bool fork = overlap || (!no_fork && n_mid > 0 && nb > n_mid);
+        cudaStream_t reg_st = aux_st, clu_st = aux_st;
+        if (overlap) {
+            clu_st = ctx->fork_stream;
+        } else if (fork) {
             SCTDA_CUDA(ctx, cudaEventRecord(ctx->fork_ev[0], aux_st));
             SCTDA_CUDA(ctx, cudaStreamWaitEvent(ctx->fork_stream, ctx->fork_ev[0], 0));
             reg_st = ctx->fork_stream;
         }
         if (n_huge) {
             a.prob0 = 0;
-            prim_kernel<<<n_huge, 256, 16, aux_st>>>(a);
+            prim_kernel<<<n_huge, 256, 16, clu_st>>>(a);
             SCTDA_LAUNCH_CHECK(ctx, "prim_kernel");
         }
         if (n_big > n_huge) {
             a.prob0 = n_huge;
             const int mm = h_off[order[bt.pos + n_huge] + 1] - h_off[order[bt.pos + n_huge]];
-            prim_cluster_kernel<8><<<(n_big - n_huge) * kClusterCtas, 512, (size_t)mm * 8 + 16, aux_st>>>(a);
+            prim_cluster_kernel<8><<<(n_big - n_huge) * kClusterCtas, 512, (size_t)mm * 8 + 16, clu_st>>>(a);
             SCTDA_LAUNCH_CHECK(ctx, "prim_cluster_kernel<8>");
         }
         if (n_mid > n_big) {
             a.prob0 = n_big;
             const int mm = h_off[order[bt.pos + n_big] + 1] - h_off[order[bt.pos + n_big]];
-            prim_cluster_kernel<4><<<(n_mid - n_big) * kClusterCtas, 512, (size_t)mm * 8 + 16, aux_st>>>(a);
+            prim_cluster_kernel<4><<<(n_mid - n_big) * kClusterCtas, 512, (size_t)mm * 8 + 16, clu_st>>>(a);
             SCTDA_LAUNCH_CHECK(ctx, "prim_cluster_kernel<4>");
         }
         // One CTA of 512 threads per patch, keys in registers, ONE launch for every patch up to 4,096 cells:
@@ -1219,7 +1255,7 @@ extern "C" int32_t sctda_bin_cluster(sctda_ctx* ctx, int32_t G, const double* d_
             prim_reg_kernel<4, 128><<<nb - n_512, 128, (size_t)mm * 12 + 16, reg_st>>>(a);
             SCTDA_LAUNCH_CHECK(ctx, "prim_reg_kernel<4,128>");
         }
-        if (fork) {
+        if (fork) {                                   // the selection kernels need every MST
             SCTDA_CUDA(ctx, cudaEventRecord(ctx->fork_ev[1], ctx->fork_stream));
             SCTDA_CUDA(ctx, cudaStreamWaitEvent(aux_st, ctx->fork_ev[1], 0));
         }

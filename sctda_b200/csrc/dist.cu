@@ -207,6 +207,30 @@ __device__ __forceinline__ void gemm_tile(const GemmArgs& a, const GemmProblem& 
     }
 }
 
+// Tile t (global index over the upper-triangular tiles of all patches of the batch) of a batched launch.
+template <bool BULK>
+__device__ __forceinline__ void batched_tile(const GemmArgs& a, int64_t t, double* smem, uint64_t* bars, unsigned& it) {
+    int lo = 0, hi = a.nprob;                                 // last p with tile_prefix[p] <= t
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (a.tile_prefix[mid] <= t) lo = mid; else hi = mid;
+    }
+    const int bin = a.prob_bin[lo];
+    const int m = a.bin_off[bin + 1] - a.bin_off[bin];
+    const int tn = (m + BN - 1) / BN;
+    int64_t lt = t - a.tile_prefix[lo];                      // index into the upper triangle of tiles, row-major
+    int ti = 0;
+    while (lt >= tn - ti) { lt -= tn - ti; ++ti; }
+    const int tj = ti + (int)lt;
+    GemmProblem pr;
+    pr.rows_a = pr.rows_b = a.members + a.bin_off[bin];
+    pr.row0_a = pr.row0_b = 0;
+    pr.na = pr.nb = m;
+    pr.out = a.gram + a.gram_off[lo];
+    pr.ldo = m;
+    gemm_tile<BULK>(a, pr, ti, tj, smem, ti != tj, bars, it);
+}
+
 template <bool BULK>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(GemmArgs a) {
     extern __shared__ __align__(16) double smem[];
@@ -236,27 +260,20 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(GemmArgs a) {
             gemm_tile<BULK>(a, a.single, (int)(t / tn), (int)(t % tn), smem, false, bars, it);
         return;
     }
-    const int64_t total = a.tile_prefix[a.nprob];
-    for (int64_t t = blockIdx.x; t < total; t += gridDim.x) {
-        int lo = 0, hi = a.nprob;                             // last p with tile_prefix[p] <= t
-        while (hi - lo > 1) {
-            int mid = (lo + hi) >> 1;
-            if (a.tile_prefix[mid] <= t) lo = mid; else hi = mid;
-        }
-        const int bin = a.prob_bin[lo];
-        const int m = a.bin_off[bin + 1] - a.bin_off[bin];
-        const int tn = (m + BN - 1) / BN;
-        int64_t lt = t - a.tile_prefix[lo];                  // index into the upper triangle of tiles, row-major
-        int ti = 0;
-        while (lt >= tn - ti) { lt -= tn - ti; ++ti; }
-        const int tj = ti + (int)lt;
-        GemmProblem pr;
-        pr.rows_a = pr.rows_b = a.members + a.bin_off[bin];
-        pr.row0_a = pr.row0_b = 0;
-        pr.na = pr.nb = m;
-        pr.out = a.gram + a.gram_off[lo];
-        pr.ldo = m;
-        gemm_tile<BULK>(a, pr, ti, tj, smem, ti != tj, bars, it);
+    const int pb = a.prob_end > 0 ? a.prob_begin : 0, pe = a.prob_end > 0 ? a.prob_end : a.nprob;
+    const int64_t first = a.tile_prefix[pb], total = a.tile_prefix[pe];
+    if (!a.tile_counter) {                                    // static striding over the tiles of the launch
+        for (int64_t t = first + blockIdx.x; t < total; t += gridDim.x) batched_tile<BULK>(a, t, smem, bars, it);
+        return;
+    }
+    __shared__ long long s_tile;                              // dynamic: tiles are claimed in order from a global counter
+    for (int done = 0; a.tiles_per_cta == 0 || done < a.tiles_per_cta; ++done) {
+        __syncthreads();                                      // the previous tile's readers of s_tile are done
+        if (threadIdx.x == 0) s_tile = (long long)(first + (int64_t)atomicAdd(a.tile_counter, 1ull));
+        __syncthreads();
+        const int64_t t = s_tile;
+        if (t >= total) break;
+        batched_tile<BULK>(a, t, smem, bars, it);
     }
 }
 
@@ -311,7 +328,13 @@ int launch_gemm(sctda_ctx* ctx, const GemmArgs& a, int64_t tiles_hint, cudaStrea
     }
     int64_t grid = tiles_hint > 0 ? tiles_hint : ctx->sm_count;
     if (grid > ctx->sm_count) grid = ctx->sm_count;          // persistent: one CTA per SM
+    if (a.grid_ctas > 0) grid = a.grid_ctas;
     if (grid < 1) grid = 1;
+    if (a.untimed) {
+        gemm_kernel<false><<<(unsigned)grid, GEMM_THREADS, GEMM_SMEM, st>>>(a);
+        SCTDA_LAUNCH_CHECK(ctx, "gemm_kernel");
+        return SCTDA_OK;
+    }
     SCTDA_TIME_BEGIN(ctx, st);
     // Measured on B200 (config 2 / config 3 patch Gram matrices): the TMA bulk-copy staging is 22 %
     // SLOWER than 16-byte cp.async for these 128-byte gathered row segments (UBLKCP is a
@@ -331,12 +354,15 @@ int launch_gemm(sctda_ctx* ctx, const GemmArgs& a, int64_t tiles_hint, cudaStrea
 int sctda_internal_gram_bins(sctda_ctx* ctx, int G, const double* d_Xn, int64_t ldxn, int nbins,
                              const int32_t* d_prob_bin, const int32_t* d_bin_off, const int32_t* d_members,
                              const int64_t* d_tile_prefix, const int64_t* d_gram_off, double* d_gram, cudaStream_t st,
-                             int64_t nrows, bool reuse_split) {
+                             int64_t nrows, bool reuse_split, int prob_begin, int prob_end, unsigned long long* d_tile_counter,
+                             int grid_ctas, bool untimed, int tiles_per_cta) {
     GemmArgs a;
     memset(&a, 0, sizeof(a));
     a.X = d_Xn; a.ldx = ldxn; a.G = G; a.epilogue = EPI_GRAM; a.nrows = nrows;
     a.nprob = nbins; a.prob_bin = d_prob_bin; a.bin_off = d_bin_off; a.members = d_members;
     a.tile_prefix = d_tile_prefix; a.gram_off = d_gram_off; a.gram = d_gram;
+    a.prob_begin = prob_begin; a.prob_end = prob_end; a.tile_counter = d_tile_counter;
+    a.grid_ctas = grid_ctas; a.untimed = untimed ? 1 : 0; a.tiles_per_cta = tiles_per_cta;
     return launch_gemm(ctx, a, 0, st, ldxn >= ((int64_t)G + 15) / 16 * 16, reuse_split);
 }
 

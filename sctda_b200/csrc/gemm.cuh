@@ -32,6 +32,15 @@ struct GemmArgs {
     const int64_t* tile_prefix;  // [nprob+1] number of upper-triangular 128x128 tiles before problem p
     const int64_t* gram_off;     // [nprob+1] element offset of problem p's m x m output
     double* gram;
+    // FP64 kernel only: the launch covers the tiles of problems [prob_begin, prob_end) (0, 0 = all), and with a
+    // counter (zeroed by the host) the CTAs claim tiles from it instead of striding: a launch that shares the
+    // GPU with long-running MST kernels must not leave tiles to CTAs that start late
+    int prob_begin, prob_end;
+    unsigned long long* tile_counter;
+    int grid_ctas;               // host: CTAs of the launch (0 = one per SM)
+    int tiles_per_cta;           // with a tile counter: a CTA retires after this many tiles (0 = runs until the counter is
+                                 // exhausted), so that SMs turn over and kernels of a higher-priority stream get in
+    int untimed;                 // host: a helper launch on another stream, not bracketed by the call's timing events
 };
 
 
