@@ -75,6 +75,15 @@ int64_t sctda_launch_count(const sctda_ctx* ctx);
 int32_t sctda_set_precision(sctda_ctx* ctx, int32_t mode);
 int32_t sctda_get_precision(const sctda_ctx* ctx);
 
+/* Linkage of the per-patch agglomerative clustering (mapper_graph(clust='agglomerative'), ref:758-771;
+ * sakmapper hands the patch to sklearn.cluster.AgglomerativeClustering, whose linkage the call sites do not pin):
+ *   0  single linkage: the minimum spanning tree of the patch (Prim kernels), the DEFAULT
+ *   1  average, 2  Ward, 3  complete: nearest-neighbour chain with Lance-Williams updates on a working copy of the
+ *      patch's distance matrix (one CTA per patch; twice the matrix memory per batch).
+ * The model selection (Davies-Bouldin over K = 2..K_max, or the histogram-gap cut) is the same for all four. */
+int32_t sctda_set_linkage(sctda_ctx* ctx, int32_t mode);
+int32_t sctda_get_linkage(const sctda_ctx* ctx);
+
 /* Measurement aid (bench.py "roofline"): when enabled, every hot-path call brackets its
  * DOMINANT kernel (conn_perm_kernel for sctda_conn_perm_test) with CUDA events on the
  * caller's stream.  sctda_last_kernel_ms waits for that kernel to finish (host sync on

@@ -264,12 +264,40 @@ def db_index_from_gram(Gm, fine_labels, coarse_of_fine):
     return tot / float(K)
 
 
-def cluster_bin(Gm, max_K=5, stat='db', hist_bins=10):
+def linkage_tree(Gm, linkage):
+    """Average / Ward / complete linkage of one bin (scipy.cluster.hierarchy.linkage on the Euclidean distances
+    read off the Gram matrix) in the form prim_mst returns for single linkage: the cluster that disappears in a
+    merge is a vertex hanging under the surviving one (the cluster containing the smaller smallest member),
+    with the squared merge height as edge weight and the merge index as insertion order."""
+    import scipy.cluster.hierarchy
+    import scipy.spatial.distance
+    m = Gm.shape[0]
+    g = numpy.diag(Gm)
+    d2 = numpy.maximum((g[:, None] + g[None, :]) - 2.0 * Gm, 0.0)
+    d = numpy.sqrt(d2)
+    numpy.fill_diagonal(d, 0.0)
+    Z = scipy.cluster.hierarchy.linkage(scipy.spatial.distance.squareform(0.5 * (d + d.T), checks=False), method=linkage)
+    rep = list(range(m)) + [0] * (m - 1)          # smallest member of every (original or merged) cluster
+    parent = numpy.full(m, -1, dtype=numpy.int64)
+    weight = numpy.zeros(m)
+    order = numpy.full(m, -1, dtype=numpy.int64)
+    for t in range(m - 1):
+        a, b = int(Z[t, 0]), int(Z[t, 1])
+        ra, rb = rep[a], rep[b]
+        keep, gone = (ra, rb) if ra < rb else (rb, ra)
+        parent[gone] = keep
+        weight[gone] = Z[t, 2] ** 2
+        order[gone] = t
+        rep[m + t] = keep
+    return parent, weight, order
+
+
+def cluster_bin(Gm, max_K=5, stat='db', hist_bins=10, linkage='single'):
     """Labels (0..K-1, clusters numbered by smallest member) of one bin from its Gram matrix."""
     m = Gm.shape[0]
     if m == 1:
         return numpy.zeros(1, dtype=numpy.int64), 1, []
-    parent, weight, order = prim_mst(Gm)
+    parent, weight, order = prim_mst(Gm) if linkage == 'single' else linkage_tree(Gm, linkage)
     if stat == 'histgap':
         h = numpy.sqrt(weight[1:])
         lo, hi = h.min(), h.max()
@@ -317,7 +345,7 @@ def nerve(clusters):
 
 
 def mapper_graph(X, lens, resolution, gain, equalize=True, clust='agglomerative', stat='db', max_K=5,
-                 metric='euclidean', verbose=False):
+                 metric='euclidean', verbose=False, linkage='single'):
     """The sakmapper.mapper_graph contract (ref:768-771): returns (edges, all_clusters, patches)
     with all_clusters[k] = ascending cell rows of node k and patches[b] = cell rows of bin b."""
     if clust != 'agglomerative':
@@ -334,7 +362,7 @@ def mapper_graph(X, lens, resolution, gain, equalize=True, clust='agglomerative'
             continue
         n_patch += 1
         Gm = gram(Xn, cells, cells)
-        labels, K, _ = cluster_bin(Gm, max_K=max_K, stat=stat)
+        labels, K, _ = cluster_bin(Gm, max_K=max_K, stat=stat, linkage=linkage)
         for c in range(K):
             all_clusters.append(cells[labels == c])
             node_bin.append(b)

@@ -42,6 +42,8 @@ SIGNATURES = {
     'sctda_launch_count': (c_i64, [c_ptr]),
     'sctda_set_precision': (c_i32, [c_ptr, c_i32]),
     'sctda_get_precision': (c_i32, [c_ptr]),
+    'sctda_set_linkage': (c_i32, [c_ptr, c_i32]),
+    'sctda_get_linkage': (c_i32, [c_ptr]),
     'sctda_set_kernel_timing': (c_i32, [c_ptr, c_i32]),
     'sctda_last_kernel_ms': (c_i32, [c_ptr, ctypes.POINTER(ctypes.c_float)]),
     'sctda_row_normalize_f64': (c_i32, [c_ptr, c_i32, c_i32, c_ptr, c_i64, c_i32, c_ptr, c_i64, c_ptr, c_ptr]),
@@ -153,6 +155,25 @@ class Context(object):
                 yield self
             finally:
                 self.set_precision(old)
+        return scope()
+
+    LINKAGES = {'single': 0, 'average': 1, 'ward': 2, 'complete': 3}
+
+    def linkage(self, mode):
+        """Context manager: `with ctx.linkage('ward'): ...` — the linkage of the per-patch agglomerative clustering
+        (sctda_set_linkage; 'single' is the default), restored on exit."""
+        import contextlib
+        if mode not in self.LINKAGES:
+            raise ValueError("linkage must be one of %s, got %r" % (sorted(self.LINKAGES), mode))
+
+        @contextlib.contextmanager
+        def scope():
+            old = int(self.lib.sctda_get_linkage(self.handle))
+            self.check(self.lib.sctda_set_linkage(self.handle, self.LINKAGES[mode]))
+            try:
+                yield self
+            finally:
+                self.check(self.lib.sctda_set_linkage(self.handle, old))
         return scope()
 
     def get_precision(self):

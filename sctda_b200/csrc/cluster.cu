@@ -140,6 +140,8 @@ struct ClusterArgs {
     int32_t* labels;          // out [Mtot]
     int32_t* bin_K;           // out [nbins]
     double* bin_db;           // out [nbins][kMaxK] Davies-Bouldin score of K = 2.. (NaN where not evaluated)
+    double* dmat;             // linkage != single: working distance matrices, same offsets as `gram`
+    int linkage;              // 0 single (MST kernels), 1 average, 2 ward, 3 complete (linkage_kernel)
 };
 
 __device__ __forceinline__ double dist2(double gpp_u, double gpp_q, double g) {
@@ -451,6 +453,135 @@ __device__ __forceinline__ double warp_masked_seq_sum(const double* __restrict__
         x1 = x2;
     }
     return acc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Average / Ward / complete linkage of one patch (cluster='agglomerative' with sklearn's other linkages,
+// /root/reference/scTDA/main.py:758-771): nearest-neighbour chain with Lance-Williams updates on a working copy
+// of the patch's distance matrix.  One CTA per patch; every step is one block-wide argmin over a matrix row.
+//   init     D[i][j] = squared Euclidean distance from the Gram tile (Ward), or its square root (average, complete)
+//   chain    follow nearest neighbours (ties: the previous chain element first, then the smallest index) until two
+//            clusters are mutually nearest; merge them into the slot of smaller index
+//   update   average  d(k, ab) = (n_a d(k,a) + n_b d(k,b)) / (n_a + n_b)
+//            Ward     d2(k, ab) = ((n_a+n_k) d2(k,a) + (n_b+n_k) d2(k,b) - n_k d2(a,b)) / (n_a+n_b+n_k)
+//            complete d(k, ab) = max(d(k,a), d(k,b))
+// All three are reducible: the chain's merges, ordered by height, are the dendrogram.  The merge tree is written
+// in the form the single-linkage MST has (parent / weight / insertion order / insertion sequence): the slot that
+// disappears in a merge is a vertex whose parent is the surviving slot and whose edge weight is the squared merge
+// height; the sequence lists the last survivor first and then the slots in reverse order of disappearance.
+// Removing the K-1 heaviest edges of that tree leaves the K clusters of the dendrogram, so labels_kernel, the
+// Davies-Bouldin selection and the histogram-gap cut run unchanged on it.
+// ------------------------------------------------------------------------------------------------
+constexpr int kLinkThreads = 1024;
+
+__global__ void __launch_bounds__(kLinkThreads) linkage_kernel(ClusterArgs a) {
+    __shared__ double s_v[32];
+    __shared__ int s_i[32];
+    __shared__ int s_pick;
+    __shared__ double s_pickv;
+    const int prob = a.prob0 + blockIdx.x;
+    const int b = a.prob_bin[prob];
+    const int off = a.bin_off[b], m = a.bin_off[b + 1] - off;
+    if (m < 2) {
+        if (m == 1 && threadIdx.x == 0) { a.mst_parent[off] = -1; a.mst_order[off] = -1; a.mst_seq[off] = 0; a.mst_w[off] = 0.0; }
+        return;
+    }
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double* Gm = a.gram + a.gram_off[prob];
+    double* D = a.dmat + a.gram_off[prob];
+    double* size = a.dist + off;                 // cluster size of an active slot, 0 for a slot that is gone
+    int32_t* chain = a.ppar + off;
+    int32_t* par = a.mst_parent + off;
+    int32_t* ord = a.mst_order + off;
+    int32_t* seq = a.mst_seq + off;
+    double* w = a.mst_w + off;
+    const bool ward = a.linkage == 2;
+    for (int64_t e = tid; e < (int64_t)m * m; e += kLinkThreads) {
+        const int i = (int)(e / m), j = (int)(e % m);
+        const double d2 = dist2(Gm[(int64_t)i * m + i], Gm[(int64_t)j * m + j], Gm[e]);
+        D[e] = ward ? d2 : sqrt(d2);
+    }
+    for (int v = tid; v < m; v += kLinkThreads) { size[v] = 1.0; par[v] = -1; ord[v] = -1; w[v] = 0.0; }
+    __syncthreads();
+    int chain_len = 0, cursor = 0, merges = 0;   // (uniform across the CTA)
+    while (merges < m - 1) {
+        if (chain_len == 0) {
+            while (size[cursor] == 0.0) ++cursor;         // the lowest active slot starts a chain
+            if (tid == 0) chain[0] = cursor;
+            chain_len = 1;
+            __syncthreads();
+        }
+        const int x = chain[chain_len - 1];
+        const int prev = chain_len > 1 ? chain[chain_len - 2] : -1;
+        // nearest active neighbour of x: smallest distance, the previous chain element wins ties, then the smallest index
+        const double* row = D + (int64_t)x * m;
+        double bv = INFINITY;
+        int bi = 0x7fffffff;
+        for (int j = tid; j < m; j += kLinkThreads) {
+            if (j == x || size[j] == 0.0) continue;
+            const double d = row[j];
+            if (d < bv || (d == bv && (j == prev || (bi != prev && j < bi)))) { bv = d; bi = j; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov < bv || (ov == bv && oi != bi && (oi == prev || (bi != prev && oi < bi)))) { bv = ov; bi = oi; }
+        }
+        if (lane == 0) { s_v[warp] = bv; s_i[warp] = bi; }
+        __syncthreads();
+        if (tid == 0) {
+            for (int k = 1; k < kLinkThreads / 32; ++k) {
+                const double ov = s_v[k];
+                const int oi = s_i[k];
+                if (ov < bv || (ov == bv && oi != bi && (oi == prev || (bi != prev && oi < bi)))) { bv = ov; bi = oi; }
+            }
+            s_pick = bi;
+            s_pickv = bv;
+        }
+        __syncthreads();
+        const int y = s_pick;
+        const double dxy = s_pickv;
+        if (y != prev) {                                   // grow the chain
+            if (tid == 0) chain[chain_len] = y;
+            ++chain_len;
+            __syncthreads();
+            continue;
+        }
+        // x and y are mutually nearest: merge into the slot of smaller index
+        const int keep = min(x, y), gone = max(x, y);
+        const double na = size[keep], nb = size[gone];
+        const double* rk = D + (int64_t)keep * m;
+        const double* rg = D + (int64_t)gone * m;
+        __syncthreads();                                   // every thread has read size[] of this step
+        for (int k = tid; k < m; k += kLinkThreads) {
+            const double nk = size[k];
+            if (k == keep || k == gone || nk == 0.0) continue;
+            const double dk = rk[k], dg = rg[k];
+            double d;
+            if (a.linkage == 1) d = (na * dk + nb * dg) / (na + nb);
+            else if (a.linkage == 2) d = ((na + nk) * dk + (nb + nk) * dg - nk * dxy) / (na + nb + nk);
+            else d = fmax(dk, dg);
+            D[(int64_t)keep * m + k] = d;
+            D[(int64_t)k * m + keep] = d;
+        }
+        if (tid == 0) {
+            size[keep] = na + nb;
+            size[gone] = 0.0;
+            par[gone] = keep;
+            ord[gone] = merges;                            // chronological index of the merge
+            w[gone] = ward ? dxy : dxy * dxy;              // squared height, like the MST's squared edge lengths
+            seq[m - 1 - merges] = gone;                    // reverse order of disappearance; seq[0] is filled at the end
+        }
+        ++merges;
+        chain_len -= 2;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        int root = 0;
+        while (size[root] == 0.0) ++root;
+        seq[0] = root;
+    }
 }
 
 constexpr int kSelThreads = 1024;
@@ -1044,6 +1175,8 @@ extern "C" int32_t sctda_bin_cluster(sctda_ctx* ctx, int32_t G, const double* d_
         if (budget > ((size_t)16 << 30)) budget = (size_t)16 << 30;
         if (budget < ((size_t)256 << 20)) budget = (size_t)256 << 20;
     }
+    const int linkage = ctx->linkage;             // 0 single (MST), 1 average, 2 ward, 3 complete (sctda_set_linkage)
+    if (linkage != 0) budget /= 2;                // the chain works on a copy of every patch's distance matrix
     const size_t aux_bytes = M * (8 * (2 * kMaxK + 4) + 4 * 4 + (kMaxK - 1)) + 256;
     unsigned char* aux = (unsigned char*)sctda_ws(ctx, WS_CLUSTER3, aux_bytes);
     if (!aux) return SCTDA_ERR_NOMEM;
@@ -1061,6 +1194,7 @@ extern "C" int32_t sctda_bin_cluster(sctda_ctx* ctx, int32_t G, const double* d_
     a.ppar = a.mst_seq + M;
     a.lev_g = (int8_t*)(a.ppar + M);
     a.labels = d_labels; a.bin_K = d_bin_K; a.bin_db = db;
+    a.linkage = linkage; a.dmat = nullptr;
     a.prim_cap = 0;                               // the generic kernel keeps its state in global memory
     a.lev_cap = 160 * 1024 - 16;                  // bytes of shared memory for the level labels, (max_K - 1) * m per patch
     if (!(ctx->attr_done & 1u)) {
@@ -1123,7 +1257,7 @@ extern "C" int32_t sctda_bin_cluster(sctda_ctx* ctx, int32_t G, const double* d_
     // B200 it gains 1 % on a 4-batch build and makes single-batch builds jitter by up to +30 % (the
     // cross-stream hand-over), so it is opt-in (SCTDA_PIPELINE=1, at least two batches) and the
     // default runs every kernel on the caller's stream.
-    const bool pipe = batches.size() >= 2 && getenv("SCTDA_PIPELINE") && atoi(getenv("SCTDA_PIPELINE")) != 0;
+    const bool pipe = linkage == 0 && batches.size() >= 2 && getenv("SCTDA_PIPELINE") && atoi(getenv("SCTDA_PIPELINE")) != 0;
     cudaStream_t aux_st = pipe ? ctx->aux_stream : st;
     // allocate both buffers up front (no reallocation while the pipeline runs)
     size_t need0 = 0, need1 = 0, meta0 = 0, meta1 = 0;
@@ -1137,6 +1271,11 @@ extern "C" int32_t sctda_bin_cluster(sctda_ctx* ctx, int32_t G, const double* d_
     unsigned char* meta_buf[2] = {(unsigned char*)sctda_ws(ctx, WS_CLUSTER, meta0),
                                   meta1 ? (unsigned char*)sctda_ws(ctx, WS_CLUSTER5, meta1) : nullptr};
     if (!gram_buf[0] || !meta_buf[0] || (need1 && (!gram_buf[1] || !meta_buf[1]))) return SCTDA_ERR_NOMEM;
+    double* dmat_buf = nullptr;
+    if (linkage != 0) {                            // one working matrix buffer, as large as the largest batch
+        dmat_buf = (double*)sctda_ws(ctx, WS_LINK, std::max(need0, need1));
+        if (!dmat_buf) return SCTDA_ERR_NOMEM;
+    }
     for (size_t i = 0; i < batches.size(); ++i) {
         const Batch& bt = batches[i];
         const int k = (int)(i & 1);
@@ -1214,7 +1353,14 @@ extern "C" int32_t sctda_bin_cluster(sctda_ctx* ctx, int32_t G, const double* d_
             SCTDA_CUDA(ctx, cudaStreamWaitEvent(ctx->fork_stream, ctx->fork_ev[0], 0));
             reg_st = ctx->fork_stream;
         }
-        if (n_huge) {
+        if (linkage != 0) {                           // average / Ward / complete: one nearest-neighbour chain per patch
+            a.prob0 = 0;
+            a.dmat = dmat_buf;
+            linkage_kernel<<<nb, kLinkThreads, 0, aux_st>>>(a);
+            SCTDA_LAUNCH_CHECK(ctx, "linkage_kernel");
+            n_huge = n_big = n_mid = n_1k = n_512 = nb;         // no MST launches below
+        }
+        if (n_huge && linkage == 0) {
             a.prob0 = 0;
             prim_kernel<<<n_huge, 256, 16, clu_st>>>(a);
             SCTDA_LAUNCH_CHECK(ctx, "prim_kernel");

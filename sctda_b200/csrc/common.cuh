@@ -26,6 +26,7 @@ struct sctda_ctx {
     cudaStream_t fork_stream;            // MST size classes run side by side (cluster.cu)
     cudaEvent_t fork_ev[2];
     int precision;                       // sctda_set_precision: 0 = FP64 (bit-exact, default), 1 = 3xTF32 contraction
+    int linkage;                         // sctda_set_linkage: 0 single (default), 1 average, 2 ward, 3 complete
 };
 
 // Workspace slots (one live use per call; calls on one context are serialised by contract).
@@ -43,6 +44,8 @@ enum {
     WS_CLUSTER5 = 11,   // second batch-metadata buffer
     WS_MISC2 = 13,
     WS_SPLIT = 12,      // (hi, lo) TF32 operands of the opt-in 3xTF32 contraction
+    WS_LINK = 14,       // working distance matrices of the non-single linkages (shared with the PCA lens' Gram matrix:
+                        // the two never run inside one call)
 };
 
 static inline int sctda_fail(sctda_ctx* ctx, int code, const char* fmt, const char* a = "", long long b = 0) {

@@ -71,6 +71,15 @@ extern "C" int32_t sctda_set_precision(sctda_ctx* ctx, int32_t mode) {
 
 extern "C" int32_t sctda_get_precision(const sctda_ctx* ctx) { return ctx ? ctx->precision : SCTDA_ERR_INVALID; }
 
+extern "C" int32_t sctda_set_linkage(sctda_ctx* ctx, int32_t mode) {
+    if (!ctx) return SCTDA_ERR_INVALID;
+    if (mode < 0 || mode > 3) return sctda_fail(ctx, SCTDA_ERR_UNSUPPORTED, "set_linkage: 0 single, 1 average, 2 ward, 3 complete%s");
+    ctx->linkage = mode;
+    return SCTDA_OK;
+}
+
+extern "C" int32_t sctda_get_linkage(const sctda_ctx* ctx) { return ctx ? ctx->linkage : SCTDA_ERR_INVALID; }
+
 extern "C" int32_t sctda_set_kernel_timing(sctda_ctx* ctx, int32_t enabled) {
     if (!ctx) return SCTDA_ERR_INVALID;
     if (enabled && !ctx->tev[0]) {

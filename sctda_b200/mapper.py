@@ -208,9 +208,13 @@ class MapperDeviceResult(object):
 
 
 def build_graph_device(ctx, Xd, lens, resolution, gain, equalize=True, stat='db', max_K=5, metric='euclidean',
-                       bounds=None, profile=None):
+                       bounds=None, profile=None, linkage='single'):
     """normalise -> cover -> per-patch clustering -> nodes -> nerve, everything on the device.
-    Xd: [N, G] float64 device tensor (even leading dimension); lens: [N, 2] host or device."""
+    Xd: [N, G] float64 device tensor (even leading dimension); lens: [N, 2] host or device;
+    linkage: 'single' (default), 'average', 'ward' or 'complete' (sctda_set_linkage)."""
+    if linkage != 'single':
+        with ctx.linkage(linkage):
+            return build_graph_device(ctx, Xd, lens, resolution, gain, equalize, stat, max_K, metric, bounds, profile)
     dev = Xd.device
     N, G = Xd.shape
     r = int(resolution)
@@ -494,22 +498,29 @@ def pca_lens_device(Xd, ctx=None, tol=1e-12, max_iter=1000, return_info=False):
 
 
 def mapper_graph(df, lens_data, resolution=10, gain=0.5, equalize=True, clust='agglomerative', stat='db', max_K=5,
-                 metric='euclidean', device=0, verbose=True, precision='fp64'):
+                 metric='euclidean', device=0, verbose=True, precision='fp64', linkage='single'):
     """sakmapper.mapper_graph as called at ref:768-771 -> (G, all_clusters, patches):
     G networkx.Graph with nodes 0..V-1 and weight-1.0 edges, all_clusters[k] the ascending row
     positions of node k, patches {(i, j): row positions of cover patch (i, j)}.
     `metric` (extension): distances used by the per-patch clustering.
     `precision` (extension): 'fp64' (default, graph identical to the oracle) or 'fp16x3' (opt-in
-    tcgen05 contraction, distances within 1e-5; see include/sctda_b200.h sctda_set_precision)."""
+    tcgen05 contraction, distances within 1e-5; see include/sctda_b200.h sctda_set_precision).
+    `linkage` (extension): the linkage of clust='agglomerative'.  sakmapper passes the patch to
+    sklearn.cluster.AgglomerativeClustering and its linkage is NOT pinned by the reference's call sites
+    (SURVEY.md appendix C.2): 'single' (default: the minimum spanning tree, north_star (2)), 'average', 'ward'
+    (sklearn's own default) or 'complete'.  clust='kmeans' and stat='gap' are randomised procedures and are
+    not offered."""
     import networkx
     if clust != 'agglomerative':
-        raise NotImplementedError("clust=%r: the device path clusters by single linkage ('agglomerative')" % (clust,))
+        raise NotImplementedError("clust=%r: the device path offers clust='agglomerative' (linkage='single', 'average', "
+                                  "'ward' or 'complete'); KMeans is randomised and not offered" % (clust,))
     ctx = _lib.context(device)
     dev = torch.device('cuda', device)
     Xd = _padded_device_table(_values(df), dev)
     lens = numpy.asarray(_values(lens_data), dtype=numpy.float64)[:, :2]
     with ctx.precision(precision):
-        res = build_graph_device(ctx, Xd, lens, resolution, gain, equalize=equalize, stat=stat, max_K=max_K, metric=metric)
+        res = build_graph_device(ctx, Xd, lens, resolution, gain, equalize=equalize, stat=stat, max_K=max_K, metric=metric,
+                                 linkage=linkage)
     bin_off = res.bin_off.cpu().numpy()
     members = res.members.cpu().numpy()
     node_off = res.node_off.cpu().numpy()
@@ -550,13 +561,14 @@ class TopologicalRepresentation(object):
             self.lens_data_mds = apply_lens(self.df, lens=lens, device=device, **kwargs)
 
     def save(self, name, resolution, gain, equalize=True, cluster='agglomerative', statistics='db', max_K=5, *,
-             cluster_metric='euclidean', precision='fp64'):
+             cluster_metric='euclidean', precision='fp64', linkage='single'):
         """ref:758-778: writes name.json and name.gexf, returns the patches.  The positional signature is
-        the reference's; `cluster_metric` and `precision` are keyword-only extensions (the opt-in
-        contraction precision of include/sctda_b200.h)."""
+        the reference's; `cluster_metric`, `precision` and `linkage` are keyword-only extensions (the
+        opt-in contraction precision and the linkage of cluster='agglomerative', see mapper_graph)."""
         G, all_clusters, patches = mapper_graph(self.df, lens_data=self.lens_data_mds, resolution=resolution, gain=gain,
                                                 equalize=equalize, clust=cluster, stat=statistics, max_K=max_K,
-                                                metric=cluster_metric, device=self.device, precision=precision)
+                                                metric=cluster_metric, device=self.device, precision=precision,
+                                                linkage=linkage)
         formats.write_mapper_json(name + '.json', all_clusters)                  # ref:772-776
         formats.write_gexf(name + '.gexf', G.number_of_nodes(), sorted(G.edges()))   # ref:777
         return patches

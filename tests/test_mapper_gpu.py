@@ -158,6 +158,57 @@ def test_graph_identical_to_oracle_5k_cells():
         assert [tuple(e) for e in res.edges.cpu().numpy().tolist()] == edges
 
 
+@pytest.mark.parametrize('linkage', ['average', 'ward', 'complete'])
+@pytest.mark.parametrize('case', [(600, 80, 5, 0.6, 'euclidean', 'db'), (900, 64, 4, 1.0, 'correlation', 'db'),
+                                  (500, 50, 3, 0.5, 'euclidean', 'histgap')])
+def test_other_linkages_match_oracle_and_sklearn(linkage, case):
+    """cluster='agglomerative' with sklearn's other linkages (ref:758-771; linkage_kernel: nearest-neighbour chain
+    with Lance-Williams updates): node lists, K and edges equal the oracle's (scipy.cluster.hierarchy.linkage on
+    the same distances + the same model selection), and on euclidean patches the chosen partitions equal
+    sklearn.cluster.AgglomerativeClustering(linkage=...) + davies_bouldin_score on the feature rows."""
+    import sklearn.cluster
+    import sklearn.metrics
+    from oracle import mapper_oracle as mo
+    from sctda_b200 import mapper
+    ctx = _gpu()
+    n, g, r, gain, metric, stat = case
+    X, lens = _data(n, g, seed=n + r + len(linkage))
+    Xd = mapper._padded_device_table(X, torch.device('cuda', 0))
+    res = mapper.build_graph_device(ctx, Xd, lens, r, gain, metric=metric, stat=stat, linkage=linkage)
+    assert ctx.lib.sctda_get_linkage(ctx.handle) == 0                      # the setting is restored
+    edges, clusters, _ = mo.mapper_graph(X, lens, r, gain, metric=metric, stat=stat, linkage=linkage)
+    node_off = res.node_off.cpu().numpy()
+    node_members = res.node_members.cpu().numpy()
+    assert res.V == len(clusters)
+    for k, c in enumerate(clusters):
+        assert list(node_members[node_off[k]:node_off[k + 1]]) == list(c)
+    assert [tuple(e) for e in res.edges.cpu().numpy().tolist()] == edges
+    if metric == 'euclidean' and stat == 'db':
+        bin_off = res.bin_off.cpu().numpy()
+        members = res.members.cpu().numpy()
+        labels = res.labels.cpu().numpy()
+        bin_K = res.bin_K.cpu().numpy()
+        for b in range(r * r):
+            cells = members[bin_off[b]:bin_off[b + 1]]
+            m = len(cells)
+            if m < 3:
+                continue
+            best = None
+            for K in range(2, (2 if m <= 5 else min(m // 2, 5)) + 1):
+                lab = sklearn.cluster.AgglomerativeClustering(n_clusters=K, linkage=linkage).fit_predict(X[cells])
+                sc = sklearn.metrics.davies_bouldin_score(X[cells], lab)
+                if best is None or sc < best[0]:
+                    best = (sc, K, lab)
+            mine = labels[bin_off[b]:bin_off[b + 1]]
+            assert sorted(sorted(int(c) for c in cells[best[2] == k]) for k in range(best[1])) == \
+                sorted(sorted(int(c) for c in cells[mine == k]) for k in range(bin_K[b]))
+    # the public seam
+    G, all_clusters, _ = mapper.mapper_graph(X, lens, r, gain, metric=metric, stat=stat, linkage=linkage, verbose=False)
+    assert G.number_of_nodes() == res.V and G.number_of_edges() == res.E
+    with pytest.raises(NotImplementedError):
+        mapper.mapper_graph(X, lens, r, gain, clust='kmeans', verbose=False)
+
+
 def test_graph_against_sklearn_single_linkage_and_davies_bouldin():
     """The whole graph against an INDEPENDENT restatement that shares nothing with the device arithmetic
     (no Gram trick, no fma chain, no lane-ordered sums): BASELINE.json configs[0]'s scale (1,000 cells x
