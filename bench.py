@@ -545,7 +545,7 @@ def run_own(a):
     tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
     if os.path.exists(tpath):
         with open(tpath) as f:
-            per_unit = json.load(f).get('conn_perm_kernel_dram_bytes_per_gene_perm')
+            per_unit = json.load(f).get('conn_perm64_kernel_dram_bytes_per_gene_perm')
         if per_unit:
             traffic = per_unit * G * a.perms
     # on-chip view: with the permutation block shared, every gene*perm gathers 8*Mtot bytes of table
@@ -560,8 +560,9 @@ def run_own(a):
             'algorithmic_bytes_per_unit': bytes_per_unit,
             'onchip': {'bound': 'l2', 'achieved': l2_ach, 'peak': l2_peak, 'unit': 'GB/s', 'frac': l2_ach / l2_peak,
                        'bytes_per_unit': l2_bytes_per_unit, 'peak_source': 'sctda_probe_l2_read_gbs in this run'},
-            'note': 'permutation block shared by all genes: index traffic is amortised over the gene shard, '
-                    'the binding resource is the L2->SM gather of 8*Mtot bytes per gene*perm (DESIGN.md)'}
+            'note': 'permutation block shared by all genes: index traffic is amortised over the gene shard; the kernel gathers '
+                    'only the 32-byte sectors of the transposed table that hold a non-zero (sector_density x 8*Mtot bytes per '
+                    'gene*perm from L2) and is bound by the latency of its dependent gather rounds and by issue (DESIGN.md)'}
 
     mapper_line = None
     if not a.no_mapper:

@@ -131,7 +131,7 @@ __device__ __forceinline__ void group8(double& acc0, double& acc1, const uint4 e
 }
 
 constexpr int kSeg = 64;          // members compacted at a time (two chunks of 32)
-constexpr int kList = kSeg + 8;   // list entries per buffer: up to 64 live members + padding to a multiple of eight
+constexpr int kList = kSeg + 16;  // list entries per buffer: up to 64 live members + padding to a multiple of sixteen
 
 // List entry of one member: x = offset of the gathered row perm[col] in 16-byte units, y = the sector mask of
 // that cell; (0, 0) for a lane beyond the segment (a zero mask is never gathered).
@@ -154,16 +154,42 @@ __device__ __forceinline__ int append_live(uint2* list, int count, uint2 pk, int
 
 // Pads the list to a multiple of eight with empty entries and makes it visible to the warp.
 __device__ __forceinline__ void close_list(uint2* list, int count, int lane) {
-    if (lane < 8) list[count + lane] = make_uint2(0u, 0u);
+    if (lane < 16) list[count + lane] = make_uint2(0u, 0u);
     __syncwarp();
 }
 
-// Sequential sums over a compacted list (member order), eight entries per gather round.
+// Sixteen members in one round: the loads of both halves are issued before any add (32 landing doubles: only
+// for the 16-warp configuration, which has the registers).
+__device__ __forceinline__ void group16(double& acc0, double& acc1, const uint4* q, unsigned lanebit, const double* base) {
+    const uint4 e0 = q[0], e1 = q[1], e2 = q[2], e3 = q[3], f0 = q[4], f1 = q[5], f2 = q[6], f3 = q[7];
+    double a[16], b[16];
+    const unsigned off[16] = {e0.x, e0.z, e1.x, e1.z, e2.x, e2.z, e3.x, e3.z, f0.x, f0.z, f1.x, f1.z, f2.x, f2.z, f3.x, f3.z};
+    const unsigned msk[16] = {e0.y, e0.w, e1.y, e1.w, e2.y, e2.w, e3.y, e3.w, f0.y, f0.w, f1.y, f1.w, f2.y, f2.w, f3.y, f3.w};
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+        asm volatile(
+            "{\n.reg .pred p;\n.reg .b32 t;\n.reg .b64 ad;\n"
+            "and.b32 t, %3, %4;\n setp.ne.u32 p, t, 0;\n"
+            "mad.wide.u32 ad, %2, 16, %5;\n"
+            "mov.f64 %0, 0d0000000000000000;\n mov.f64 %1, 0d0000000000000000;\n"
+            "@p ld.global.nc.v2.f64 {%0, %1}, [ad];\n}\n"
+            : "=d"(a[u]), "=d"(b[u]) : "r"(off[u]), "r"(msk[u]), "r"(lanebit), "l"(base));
+    }
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+        acc0 = __dadd_rn(acc0, a[u]);
+        acc1 = __dadd_rn(acc1, b[u]);
+    }
+}
+
+// Sequential sums over a compacted list (member order), GROUP entries per gather round.
+template <int GROUP>
 __device__ __forceinline__ void sum_list(double& acc0, double& acc1, const uint2* list, int count, unsigned lanebit,
                                          const double* base) {
-    for (int g = 0; g < count; g += 8) {
+    for (int g = 0; g < count; g += GROUP) {
         const uint4* q = (const uint4*)(list + g);                                          // broadcast loads
-        group8(acc0, acc1, q[0], q[1], q[2], q[3], lanebit, base);
+        if (GROUP == 16) group16(acc0, acc1, q, lanebit, base);
+        else group8(acc0, acc1, q[0], q[1], q[2], q[3], lanebit, base);
     }
     __syncwarp();
 }
@@ -290,7 +316,7 @@ __global__ void __launch_bounds__(NW * 32, 1) conn_perm64_kernel(Tile64Args a) {
                     if (lane + 32 < nn) cn1 = __ldg(a.node_cols + begn + 32 + lane);
                 }
                 double acc0 = 0.0, acc1 = 0.0;
-                sum_list(acc0, acc1, lst + cur * kList, count, lanebit, base);
+                sum_list<(NW == 16 ? 16 : 8)>(acc0, acc1, lst + cur * kList, count, lanebit, base);
                 for (int sb = beg + kSeg; sb < end; sb += kSeg) {  // nodes above 64 members: further segments, in order
                     uint2* l2 = lst + cur * kList;
                     const int ns = min(kSeg, end - sb);
@@ -299,7 +325,7 @@ __global__ void __launch_bounds__(NW * 32, 1) conn_perm64_kernel(Tile64Args a) {
                     int cnt = append_live(l2, 0, composite(perm_r, s_sec, c0, lane < ns), lane);
                     if (ns > 32) cnt = append_live(l2, cnt, composite(perm_r, s_sec, c1, lane + 32 < ns), lane);
                     close_list(l2, cnt, lane);
-                    sum_list(acc0, acc1, l2, cnt, lanebit, base);
+                    sum_list<(NW == 16 ? 16 : 8)>(acc0, acc1, l2, cnt, lanebit, base);
                 }
                 const double q = (double)len, iq = __ldg(a.inv_q + k);
                 float2 pv;
