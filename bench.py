@@ -545,7 +545,7 @@ def run_own(a):
     tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
     if os.path.exists(tpath):
         with open(tpath) as f:
-            per_unit = json.load(f).get('conn_perm64_kernel_dram_bytes_per_gene_perm')
+            per_unit = json.load(f).get('conn_perm_wide_kernel_dram_bytes_per_gene_perm')
         if per_unit:
             traffic = per_unit * G * a.perms
     # on-chip view: with the permutation block shared, every gene*perm gathers 8*Mtot bytes of table
@@ -556,13 +556,14 @@ def run_own(a):
     l2_ach = l2_bytes_per_unit * G * a.perms / (k_ms * 1e-3) / 1e9
     roof = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
             'traffic': traffic, 'traffic_note': 'bytes per launch = ncu dram__bytes_read+write per gene*perm (profiles/traffic.json) x units of this launch; algorithmic bytes per launch = algorithmic_bytes_per_unit x units',
-            'kernel': 'conn_perm64_kernel', 'kernel_ms': k_ms, 'kernel_ms_steps': [round(x, 2) for x in kernel_ms], 'peak_source': peak_src,
+            'kernel': 'conn_perm_wide_kernel', 'kernel_ms': k_ms, 'kernel_ms_steps': [round(x, 2) for x in kernel_ms], 'peak_source': peak_src,
             'algorithmic_bytes_per_unit': bytes_per_unit,
             'onchip': {'bound': 'l2', 'achieved': l2_ach, 'peak': l2_peak, 'unit': 'GB/s', 'frac': l2_ach / l2_peak,
                        'bytes_per_unit': l2_bytes_per_unit, 'peak_source': 'sctda_probe_l2_read_gbs in this run'},
             'note': 'permutation block shared by all genes: index traffic is amortised over the gene shard; the kernel gathers '
                     'only the 32-byte sectors of the transposed table that hold a non-zero (sector_density x 8*Mtot bytes per '
-                    'gene*perm from L2) and is bound by the latency of its dependent gather rounds and by issue (DESIGN.md)'}
+                    'gene*perm from L2) and is bound by the bytes it can keep in flight (register landing zone x L2 latency) '
+                    'and by the LSU data pipe (one wavefront per touched 128-byte line; DESIGN.md)'}
 
     mapper_line = None
     if not a.no_mapper:
@@ -590,7 +591,7 @@ def run_own(a):
                 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': workload_config(a, world),
                 'clocks': clocks.summary(), 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roof,
                 'cpu_baseline': cpu, 'plan_ms_untimed': plan_ms,
-                'tie_genes': int((ties > 0).sum().item()), 'mapper': mapper_line}
+                'degenerate_genes_with_exact_ties': int((ties > 0).sum().item()), 'mapper': mapper_line}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

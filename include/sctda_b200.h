@@ -122,7 +122,8 @@ typedef struct sctda_graph {
     int32_t        V;
     int32_t        S;
     int32_t        Ncells;
-    int32_t        reserved;
+    int32_t        Mtot;          /* total number of node members (= d_node_off[V]); 0 = not given: the library reads it
+                                     from the device with one synchronising 4-byte copy when it needs it */
     const int32_t* d_node_off;
     const int32_t* d_node_cols;
     const int32_t* d_adj_off;
@@ -168,10 +169,20 @@ int32_t sctda_node_stats(sctda_ctx* ctx, const sctda_graph* graph,
  *                     n*S    : a fresh block per gene, [G, n, S] (the reference's stream)
  *   d_observed        [G] float64 observed connectivity (sctda_node_stats d_conn)
  *   tie_rel           relative half-width of the band around `observed` inside which a
- *                     permuted score is also counted in d_ties (<= 0: 1e-9)
+ *                     permuted score is also counted in d_ties (<= 0: 1e-11).  The default
+ *                     covers the worst-case rounding of both evaluations of the score (a sum
+ *                     of at most nnz/2 + V float64 products, 2^-53 each: 1.3e-12 at
+ *                     nnz = 24,000) and nothing else: a count in d_ties means the permuted
+ *                     and the observed score are the same number up to rounding, which
+ *                     needs a degenerate gene (constant over the component, or expressed in
+ *                     one or two cells); the reference's own `>` is then decided by the
+ *                     summation order of its BLAS build.
  * outputs:
- *   d_exceed  [G] int32  #{r : conn_r > observed}   (p-value = exceed / n), exact integers
- *   d_ties    [G] int32  #{r : |conn_r - observed| <= tie_rel*|observed|} or NULL
+ *   d_exceed  [G] int32  #{r : conn_r > observed, not tied}   (p-value = exceed / n), exact integers
+ *   d_ties    [G] int32  #{r : |conn_r - observed| <= tie_rel*|observed|} or NULL.  A tied pair is
+ *                        the same number in exact arithmetic and is NOT counted as exceeding (strict `>`,
+ *                        ref:990), whatever the roundings of the two evaluations say: the result does not
+ *                        depend on the kernel or its summation order.
  *   d_scores  [G, n] float64 the permuted scores conn_r (ref:989) or NULL
  *
  * Arithmetic follows ref:978-989 step by step: float64 sequential member sums of

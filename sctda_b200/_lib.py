@@ -27,7 +27,7 @@ class SctdaError(RuntimeError):
 
 class Graph(ctypes.Structure):
     """struct sctda_graph."""
-    _fields_ = [('V', c_i32), ('S', c_i32), ('Ncells', c_i32), ('reserved', c_i32),
+    _fields_ = [('V', c_i32), ('S', c_i32), ('Ncells', c_i32), ('Mtot', c_i32),
                 ('d_node_off', c_ptr), ('d_node_cols', c_ptr), ('d_adj_off', c_ptr),
                 ('d_adj_idx', c_ptr), ('d_adj_w', c_ptr), ('d_samples', c_ptr)]
 

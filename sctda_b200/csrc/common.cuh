@@ -108,6 +108,12 @@ int sctda_conn_perm_tile64(sctda_ctx* ctx, const sctda_graph* gr, int G, const d
                            int n, const int32_t* d_perm, const int32_t* d_order, const double* d_observed,
                            double tie_rel, int32_t* d_exceed, int32_t* d_ties, double* d_scores, cudaStream_t st);
 
+// conn_wide.cu: the shared-permutation kernel on 128-gene tiles with per-permutation composed member indices
+bool sctda_wide_eligible(const sctda_graph* gr);
+int sctda_conn_perm_wide(sctda_ctx* ctx, const sctda_graph* gr, int G, const double* d_Y, int64_t ldy, int log2_mode,
+                         int n, const int32_t* d_perm, const int32_t* d_order, const double* d_observed,
+                         double tie_rel, int32_t* d_exceed, int32_t* d_ties, double* d_scores, cudaStream_t st);
+
 // Brackets the dominant kernel of a call with events when timing is on (see sctda_set_kernel_timing).
 #define SCTDA_TIME_RESET(ctx) do { if ((ctx)->timing) (ctx)->timed = 0; } while (0)
 #define SCTDA_TIME_BEGIN(ctx, st) do { if ((ctx)->timing && (ctx)->timed < 64) cudaEventRecord((ctx)->tev[2 * (ctx)->timed], st); } while (0)

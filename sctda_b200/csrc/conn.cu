@@ -372,8 +372,9 @@ __global__ void __launch_bounds__(NW * 32) conn_perm_kernel(PermArgs a) {
                 }
                 double conn = cor * (part / (tot * tot));
                 if (live) {
-                    if (conn > obs) ++cnt_exceed;                                      // ref:990, strict
-                    if (fabs(conn - obs) <= a.tie_rel * fabs(obs)) ++cnt_tie;
+                    const bool tied = fabs(conn - obs) <= a.tie_rel * fabs(obs);       // the same number up to rounding
+                    if (conn > obs && !tied) ++cnt_exceed;                             // ref:990, strict: a tie does not exceed
+                    if (tied) ++cnt_tie;
                     if (a.scores) a.scores[(size_t)g * a.n + r] = conn;
                 }
             }
@@ -609,6 +610,10 @@ static int32_t conn_perm_test_impl(sctda_ctx* ctx, const sctda_graph* gr, int32_
     if (n == 0) return SCTDA_OK;
     // one permutation block shared by all genes: the 64-gene sector-mask kernel (conn_tile64.cu)
     static const bool legacy = getenv("SCTDA_CONN_LEGACY") != nullptr;
+    static const bool tile64 = getenv("SCTDA_CONN_TILE64") != nullptr;
+    if (perm_gene_stride == 0 && !legacy && !tile64 && sctda_wide_eligible(gr))
+        return sctda_conn_perm_wide(ctx, gr, G, d_Y, ldy, log2_mode, n, d_perm, d_order, d_observed, tie_rel,
+                                    d_exceed, d_ties, d_scores, st);
     if (perm_gene_stride == 0 && !legacy && sctda_tile64_eligible(gr))
         return sctda_conn_perm_tile64(ctx, gr, G, d_Y, ldy, log2_mode, n, d_perm, d_order, d_observed, tie_rel,
                                       d_exceed, d_ties, d_scores, st);
@@ -634,7 +639,7 @@ static int32_t conn_perm_test_impl(sctda_ctx* ctx, const sctda_graph* gr, int32_
     a.node_off = gr->d_node_off; a.node_cols = gr->d_node_cols;
     a.adj_off = gr->d_adj_off; a.adj_idx = gr->d_adj_idx; a.adj_w = gr->d_adj_w;
     a.ET = ET; a.inv_q = inv_q; a.perm = d_perm; a.perm_gene_stride = perm_gene_stride;
-    a.observed = d_observed; a.tie_rel = tie_rel > 0.0 ? tie_rel : 1e-9;
+    a.observed = d_observed; a.tie_rel = tie_rel > 0.0 ? tie_rel : 1e-11;
     a.exceed = d_exceed; a.ties = d_ties; a.scores = d_scores; a.counter = counter;
     int64_t grid64 = (int64_t)ctx->sm_count;          // one 1024-thread CTA per SM: the node-value scratch stays in L2
     if (grid64 > a.items) grid64 = a.items;

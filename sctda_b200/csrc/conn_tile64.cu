@@ -418,13 +418,15 @@ __global__ void __launch_bounds__(NW * 32, 1) conn_perm64_kernel(Tile64Args a) {
                 }
                 const double c0 = cor * (p0 / (t0 * t0)), c1 = cor * (p1 / (t1 * t1));
                 if (g0 >= 0) {
-                    if (c0 > obs0) ++ex0;                          // ref:990, strict
-                    if (fabs(c0 - obs0) <= a.tie_rel * fabs(obs0)) ++ti0;
+                    const bool tied = fabs(c0 - obs0) <= a.tie_rel * fabs(obs0);
+                    if (c0 > obs0 && !tied) ++ex0;                 // ref:990, strict: a tie does not exceed
+                    if (tied) ++ti0;
                     if (a.scores) a.scores[(size_t)g0 * a.n + r] = c0;
                 }
                 if (g1 >= 0) {
-                    if (c1 > obs1) ++ex1;
-                    if (fabs(c1 - obs1) <= a.tie_rel * fabs(obs1)) ++ti1;
+                    const bool tied = fabs(c1 - obs1) <= a.tie_rel * fabs(obs1);
+                    if (c1 > obs1 && !tied) ++ex1;
+                    if (tied) ++ti1;
                     if (a.scores) a.scores[(size_t)g1 * a.n + r] = c1;
                 }
             }
@@ -628,7 +630,7 @@ int sctda_conn_perm_tile64(sctda_ctx* ctx, const sctda_graph* gr, int G, const d
     a.node_off = gr->d_node_off; a.node_cols = gr->d_node_cols;
     a.adj_off = gr->d_adj_off; a.adj_idx = gr->d_adj_idx; a.adj_w = gr->d_adj_w;
     a.ET = ET; a.sec = sec; a.perm16 = perm16; a.gmap = gmap; a.inv_q = inv_q;
-    a.observed = d_observed; a.tie_rel = tie_rel > 0.0 ? tie_rel : 1e-9;
+    a.observed = d_observed; a.tie_rel = tie_rel > 0.0 ? tie_rel : 1e-11;
     a.exceed = d_exceed; a.ties = d_ties; a.scores = d_scores; a.counter = counter; a.unit_w = unit_w;
     long long grid64 = ctx->sm_count;                              // one CTA per SM
     if (const char* e = getenv("SCTDA_CONN64_GRID")) grid64 = atoi(e) > 0 ? atoi(e) : grid64;

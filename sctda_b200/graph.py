@@ -103,7 +103,7 @@ class DeviceGraph(object):
         self.adj_w = torch.from_numpy(adj_csr.data.astype(numpy.float64)).to(dev)
         self.samples = torch.from_numpy(samples.astype(numpy.int32)).to(dev)
         self.device = dev
-        self.struct = _lib.Graph(V=self.V, S=self.S, Ncells=self.Ncells, reserved=0,
+        self.struct = _lib.Graph(V=self.V, S=self.S, Ncells=self.Ncells, Mtot=self.Mtot,
                                  d_node_off=self.node_off.data_ptr(), d_node_cols=self.node_cols.data_ptr(),
                                  d_adj_off=self.adj_off.data_ptr(), d_adj_idx=self.adj_idx.data_ptr(),
                                  d_adj_w=self.adj_w.data_ptr(), d_samples=self.samples.data_ptr())
@@ -133,7 +133,7 @@ def node_stats(ctx, dg, Y, log2=True, dist=None, want_p=False):
     return out
 
 
-def conn_perm_test(ctx, dg, Y, perms, observed, log2=True, per_gene=False, want_scores=False, tie_rel=1e-9,
+def conn_perm_test(ctx, dg, Y, perms, observed, log2=True, per_gene=False, want_scores=False, tie_rel=1e-11,
                    gene_order=None):
     """sctda_conn_perm_test.  Y [G, >=Ncells] float64 device; perms int32 device, [n, S]
     (shared) or [G, n, S] (per_gene); observed [G] float64 device; gene_order: int32 device

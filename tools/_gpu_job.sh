@@ -1,4 +1,4 @@
 set -x
-CMD="python tools/conn_probe.py --genes 4096 --perms 128 --order pca --reps 2"
-$CMD > gpurun_out/plain.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:conn_perm64 -s 1 -c 1 -o gpurun_out/prof_t64c -f $CMD > gpurun_out/ncu.log 2>&1
-tail -2 gpurun_out/plain.log
+python -m pytest tests -m gpu -q 2>&1 | tail -12
+P="python tools/conn_probe.py --genes 1024 --perms 1184 --order pca --reps 2"
+ncu --set full --clock-control none --import-source on -k regex:conn_perm_wide -s 1 -c 1 -o gpurun_out/prof_w4 -f $P > gpurun_out/ncu.log 2>&1
