@@ -378,8 +378,10 @@ def test_gene_gene_matrices_match_reference_golden(golden_dir, tmp_path, name):
 @pytest.mark.parametrize('n_cells', [30000, 60000])
 def test_large_components_use_the_other_staging_paths(n_cells):
     """S = 30,000: the permutation row is staged in shared memory without double buffering;
-    S = 60,000: it does not fit and is gathered from global memory.  Both must give exactly the
-    counts and scores of the per-gene path (which the oracle tests pin) on a replicated block."""
+    S = 60,000: it does not fit and is gathered from global memory (and the lane masks of the 128-gene kernel do
+    not fit its shared memory: the 64-gene kernel serves the shared block).  Both must give exactly the counts
+    of the per-gene path (which the oracle tests pin) on a replicated block, and its scores to the last bits
+    (the kernels group the partial sums of the node loop differently)."""
     ctx = _gpu()
     from sctda_b200 import graph, synth
     n_nodes, n_genes, n = 300, 40, 6
@@ -393,5 +395,5 @@ def test_large_components_use_the_other_staging_paths(n_cells):
     rep = perms.unsqueeze(0).repeat(n_genes, 1, 1).contiguous()
     exb, tib, scb = graph.conn_perm_test(ctx, dg, Yd, rep, st['conn'], per_gene=True, want_scores=True)
     assert torch.equal(exa, exb) and torch.equal(tia, tib)
-    assert torch.equal(torch.nan_to_num(sca), torch.nan_to_num(scb))
+    numpy.testing.assert_allclose(sca.cpu().numpy(), scb.cpu().numpy(), rtol=1e-13, atol=0, equal_nan=True)
     assert torch.isfinite(sca).any()
