@@ -22,6 +22,12 @@
 //     DADD into DADD + 2 FSEL, and zero-initialising costs one instruction per double);
 //   * no compaction pass: every member is one (mask test, address, predicated load, multiplier) quadruple
 //     plus four DFMAs for 128 genes.
+//   * the log table is replicated eight times so that the 16-byte lookups of a quarter warp fall into eight
+//     different bank groups whatever the indices (4 wavefronts per lookup instead of ~9).
+// Tried and dropped (bit-identical, measured on the B200): rows stored COMPACTED to their non-empty sectors
+// (a lane's sector at popc(mask & lanes below)), so that the fetched sectors are contiguous.  The LSU data pipe
+// charges one wavefront per quad of lanes with an active lane, not per 128-byte line: wavefronts per
+// gene*permutation did not move (3,900 -> 3,900) and the extra offset lookups made the kernel 40 % slower.
 // The node values, the float32 rounding of ref:972, 0.693147, the fixed reduction order (node k -> warp
 // k mod NW, partial sums combined in warp order) are those of the other two kernels.
 #include <stdlib.h>
@@ -40,6 +46,7 @@ constexpr int kSeg = 64;              // members staged at a time (two chunks of
 #endif
 constexpr int kGroup = SCTDA_CONNW_GROUP;   // members per gather round (even)
 constexpr int kList = kSeg + kGroup;  // list entries per buffer: up to 64 members + padding to a multiple of kGroup
+constexpr int kTabRep = 8;             // copies of the log table in shared memory (one per bank group)
 constexpr unsigned kGuard = 1u << 16; // half-width of the ambiguity band of pm_fast, in units of 2^-52 of the binade
 
 __device__ double2 g_logtab_w[128];   // (1/c_j rounded, -log(1/c_j rounded)), c_j = 1 + (j + 1/2)/128
@@ -55,7 +62,7 @@ __device__ __forceinline__ float pm_fast_w(double acc, double q, double inv_q, c
     const double u = 1.0 + t;
     const int hu = __double2hiint(u);
     const int k = (hu >> 20) - 1023;
-    const double2 tc = tab[(hu >> 13) & 127];
+    const double2 tc = tab[((hu >> 13) & 127) * kTabRep];                 // tab is pre-offset by lane & 7
     const double m = __hiloint2double((hu & 0x000fffff) | 0x3ff00000, __double2loint(u));
     const double r = fma(m, tc.x, -1.0);
     double p = fma(r, 0.2, -0.25);
@@ -93,7 +100,11 @@ struct WideArgs {
     double* scores;
     float* pm;                  // [grid][V][kT]
     unsigned long long* counter;
-    const int* unit_w;          // 1 when all adjacency weights are 1.0
+    const int* unit_w;          // 1 when all adjacency weights are the same number *w0
+    const double* w0;
+    const uint2* rowinfo;       // [V]: (first chunk, number of edges) of every adjacency row in ids16, or NULL
+    const uint16_t* ids16;      // adjacency rows as 16-bit node ids, every row padded to whole chunks of 8
+    const int* packed_ok;       // 1 when rowinfo / ids16 hold the whole adjacency
 };
 
 __device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src) {
@@ -237,12 +248,45 @@ __device__ __forceinline__ void spmv_rows(double (&s)[kGPL], const float* pm, in
     }
 }
 
+// Unit weights, packed rows: s += sum over the first C (1..8) edges of a chunk of 8 node ids (four registers, the
+// same in every lane) of pm[l], in edge order.  No shuffles: a SHFL costs ~1.8 wavefronts of the LSU data pipe
+// (profiles/ncu_connwide_r02.txt), three per edge in the generic path; the chunk is one 16-byte load.
+template <int C>
+__device__ __forceinline__ void spmv_ids_c(double (&s)[kGPL], const float* pm, const uint4& ids, int lane,
+                                           unsigned long long pol) {
+    const unsigned wds[4] = {ids.x, ids.y, ids.z, ids.w};
+    float4 v[C];
+#pragma unroll
+    for (int u = 0; u < C; ++u) {
+        const unsigned l = (u & 1) ? (wds[u >> 1] >> 16) : (wds[u >> 1] & 0xffffu);
+        v[u] = ld_pm(pm + (size_t)l * kT + 4 * lane, pol);
+    }
+#pragma unroll
+    for (int u = 0; u < C; ++u) {                                  // weight 1.0: w * x == x exactly
+        s[0] += (double)v[u].x; s[1] += (double)v[u].y; s[2] += (double)v[u].z; s[3] += (double)v[u].w;
+    }
+}
+
+__device__ __forceinline__ void spmv_ids(double (&s)[kGPL], const float* pm, const uint4& ids, int cnt, int lane,
+                                         unsigned long long pol) {
+    switch (cnt) {
+        case 1: spmv_ids_c<1>(s, pm, ids, lane, pol); break;
+        case 2: spmv_ids_c<2>(s, pm, ids, lane, pol); break;
+        case 3: spmv_ids_c<3>(s, pm, ids, lane, pol); break;
+        case 4: spmv_ids_c<4>(s, pm, ids, lane, pol); break;
+        case 5: spmv_ids_c<5>(s, pm, ids, lane, pol); break;
+        case 6: spmv_ids_c<6>(s, pm, ids, lane, pol); break;
+        case 7: spmv_ids_c<7>(s, pm, ids, lane, pol); break;
+        default: spmv_ids_c<8>(s, pm, ids, lane, pol); break;
+    }
+}
+
 template <int NW>
 __global__ void __launch_bounds__(NW * 32, 1) conn_perm_wide_kernel(WideArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t* s_sec = (uint32_t*)smem_raw;                        // [Sp]
-    double2* s_tab = (double2*)(s_sec + a.Sp);                    // [128]
-    double* s_tot = (double*)(s_tab + 128);                       // [NW][kT]
+    double2* s_tab = (double2*)(s_sec + a.Sp);                    // [128][kTabRep]
+    double* s_tot = (double*)(s_tab + 128 * kTabRep);             // [NW][kT]
     double* s_part = s_tot + NW * kT;                             // [NW][kT]
     uint2* s_list = (uint2*)(s_part + NW * kT);                   // [NW][2][kList]
     __shared__ long long s_claim[2];
@@ -252,9 +296,13 @@ __global__ void __launch_bounds__(NW * 32, 1) conn_perm_wide_kernel(WideArgs a) 
     const unsigned long long pol_keep = policy_evict_last(), pol_stream = policy_evict_first();
     float* pm = a.pm + (size_t)blockIdx.x * a.V * kT;
     const double cor = (double)a.V / (double)(a.V - 1);           // ref:989
-    const bool unit_w = *a.unit_w != 0;
+    const double w0 = *a.w0;
+    const bool unit_w = *a.unit_w != 0 && w0 == 1.0;
+    // one weight, 1.0 or 2.0: sum of w0 * x == w0 * (sum of x) bit for bit (scaling by a power of two is exact)
+    const bool packed = *a.unit_w != 0 && (w0 == 1.0 || w0 == 2.0) && a.rowinfo != nullptr && *a.packed_ok != 0;
     const int chunks16 = a.Sp >> 2;                               // 16-byte pieces of the mask row
-    for (int i = threadIdx.x; i < 128; i += NW * 32) s_tab[i] = g_logtab_w[i];
+    for (int i = threadIdx.x; i < 128 * kTabRep; i += NW * 32) s_tab[i] = g_logtab_w[i / kTabRep];
+    const double2* tab = s_tab + (lane & (kTabRep - 1));
     if (threadIdx.x == 0) {
         s_claim[0] = (long long)atomicAdd(a.counter, 1ull);
         s_claim[1] = (long long)atomicAdd(a.counter, 1ull);
@@ -328,10 +376,10 @@ __global__ void __launch_bounds__(NW * 32, 1) conn_perm_wide_kernel(WideArgs a) 
                 const double q = (double)len, iq = __ldg(a.inv_q + k);
                 float4 pv;
                 if (a.log2_mode) {                                 // ref:982-983, float32 store of ref:972
-                    pv.x = pm_fast_w(acc[0], q, iq, s_tab);
-                    pv.y = pm_fast_w(acc[1], q, iq, s_tab);
-                    pv.z = pm_fast_w(acc[2], q, iq, s_tab);
-                    pv.w = pm_fast_w(acc[3], q, iq, s_tab);
+                    pv.x = pm_fast_w(acc[0], q, iq, tab);
+                    pv.y = pm_fast_w(acc[1], q, iq, tab);
+                    pv.z = pm_fast_w(acc[2], q, iq, tab);
+                    pv.w = pm_fast_w(acc[3], q, iq, tab);
                 } else {                                           // ref:986
                     pv.x = (float)div_rn(acc[0], q, iq);
                     pv.y = (float)div_rn(acc[1], q, iq);
@@ -351,7 +399,43 @@ __global__ void __launch_bounds__(NW * 32, 1) conn_perm_wide_kernel(WideArgs a) 
             double part[kGPL], tot[kGPL];
 #pragma unroll
             for (int j = 0; j < kGPL; ++j) part[j] = 0.0, tot[j] = 0.0;
-            {
+            if (packed) {                                          // unit weights, rows as chunks of eight 16-bit ids
+                int kk = w;
+                uint2 ri = make_uint2(0u, 0u), rin = make_uint2(0u, 0u);
+                uint4 ids = make_uint4(0u, 0u, 0u, 0u);
+                if (kk < a.V) {
+                    ri = __ldg(a.rowinfo + kk);
+                    if (ri.y) ids = __ldg((const uint4*)(a.ids16 + (size_t)ri.x * 8));
+                }
+                if (kk + NW < a.V) rin = __ldg(a.rowinfo + kk + NW);
+                while (kk < a.V) {
+                    const int kn = kk + NW, k2 = kk + 2 * NW;
+                    uint4 idsn = make_uint4(0u, 0u, 0u, 0u);
+                    uint2 ri2 = make_uint2(0u, 0u);
+                    if (kn < a.V && rin.y) idsn = __ldg((const uint4*)(a.ids16 + (size_t)rin.x * 8));   // next row's first chunk
+                    if (k2 < a.V) ri2 = __ldg(a.rowinfo + k2);     // row header two rows ahead
+                    const float4 vk = ld_pm(pm + (size_t)kk * kT + 4 * lane, pol_stream);
+                    tot[0] += (double)vk.x;
+                    tot[1] += (double)vk.y;
+                    tot[2] += (double)vk.z;
+                    tot[3] += (double)vk.w;
+                    if (ri.y) {
+                        double s[kGPL];
+#pragma unroll
+                        for (int j = 0; j < kGPL; ++j) s[j] = 0.0;
+                        spmv_ids(s, pm, ids, min(8, (int)ri.y), lane, pol_stream);
+                        for (int c = 1; 8 * c < (int)ri.y; ++c) {  // rows with more than eight edges
+                            const uint4 more = __ldg((const uint4*)(a.ids16 + ((size_t)ri.x + c) * 8));
+                            spmv_ids(s, pm, more, min(8, (int)ri.y - 8 * c), lane, pol_stream);
+                        }
+                        part[0] += (double)vk.x * (w0 * s[0]);
+                        part[1] += (double)vk.y * (w0 * s[1]);
+                        part[2] += (double)vk.z * (w0 * s[2]);
+                        part[3] += (double)vk.w * (w0 * s[3]);
+                    }
+                    kk = kn; ri = rin; rin = ri2; ids = idsn;
+                }
+            } else {
                 int kk = w, eb = 0, ee = 0, ebn = 0, een = 0, li = 0;
                 double lw = 0.0;
                 if (kk < a.V) {
@@ -506,11 +590,47 @@ __global__ void inv_size_wide_kernel(const int32_t* __restrict__ off, int V, dou
     if (k < V) inv_q[k] = 1.0 / (double)(off[k + 1] - off[k]);
 }
 
-// *flag (preset to 1) is cleared when an edge weight differs from 1.0
-__global__ void unit_weight_wide_kernel(const int32_t* __restrict__ adj_off, int V, const double* __restrict__ w, int* flag) {
+// *flag (preset to 1) is cleared when the edge weights are not all the same number; *w0 = that number (the first
+// weight).  graph.DeviceGraph hands over triu(A + A', 1) + diag(A): 2.0 everywhere for a 0/1 adjacency without loops.
+__global__ void unit_weight_wide_kernel(const int32_t* __restrict__ adj_off, int V, const double* __restrict__ w, int* flag,
+                                        double* w0) {
     const int nnz = adj_off[V];
+    const double first = nnz > 0 ? w[0] : 1.0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *w0 = first;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += gridDim.x * blockDim.x)
-        if (w[e] != 1.0) *flag = 0;
+        if (w[e] != first) *flag = 0;
+}
+
+// Adjacency rows as 16-bit node ids in chunks of eight (the unit-weight path of the kernel): rowinfo[k] =
+// (first chunk, number of edges).  One CTA; *ok (preset to 1) is cleared when `cap` chunks do not hold the rows.
+__global__ void __launch_bounds__(1024) pack_adj_wide_kernel(const int32_t* __restrict__ adj_off,
+                                                             const int32_t* __restrict__ adj_idx, int V, unsigned cap,
+                                                             uint2* __restrict__ rowinfo, uint16_t* __restrict__ ids16,
+                                                             int* ok) {
+    __shared__ unsigned tot[1024];
+    const int t = threadIdx.x;
+    const int per = (V + 1023) / 1024;
+    const int k0 = min(V, t * per), k1 = min(V, k0 + per);
+    unsigned run = 0;
+    for (int k = k0; k < k1; ++k) run += (unsigned)(adj_off[k + 1] - adj_off[k] + 7) >> 3;
+    tot[t] = run;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {                            // inclusive scan of the per-thread chunk counts
+        const unsigned add = t >= d ? tot[t - d] : 0u;
+        __syncthreads();
+        tot[t] += add;
+        __syncthreads();
+    }
+    const bool fits = tot[1023] <= cap;
+    if (t == 0 && !fits) *ok = 0;
+    if (!fits) return;
+    unsigned c = tot[t] - run;
+    for (int k = k0; k < k1; ++k) {
+        const int eb = adj_off[k], deg = adj_off[k + 1] - eb;
+        rowinfo[k] = make_uint2(c, (unsigned)deg);
+        for (int e = 0; e < ((deg + 7) & ~7); ++e) ids16[(size_t)c * 8 + e] = e < deg ? (uint16_t)adj_idx[eb + e] : (uint16_t)0;
+        c += (unsigned)(deg + 7) >> 3;
+    }
 }
 
 int ensure_logtab_w(sctda_ctx* ctx) {
@@ -538,7 +658,7 @@ int launch_wide(sctda_ctx* ctx, const WideArgs& a, int grid, size_t smem, cudaSt
 }  // namespace
 
 static size_t wide_smem(int Sp, int NW) {
-    return (size_t)Sp * 4 + 128 * sizeof(double2) + (size_t)2 * NW * kT * sizeof(double) + (size_t)NW * 2 * kList * sizeof(uint2);
+    return (size_t)Sp * 4 + 128 * kTabRep * sizeof(double2) + (size_t)2 * NW * kT * sizeof(double) + (size_t)NW * 2 * kList * sizeof(uint2);
 }
 
 static int wide_warps() {
@@ -593,15 +713,33 @@ int sctda_conn_perm_wide(sctda_ctx* ctx, const sctda_graph* gr, int G, const dou
     const int nlaunch = (n + nblk - 1) / nblk;
     uint16_t* Lr = (uint16_t*)sctda_ws(ctx, WS_MISC2, (size_t)nblk * Mtot * sizeof(uint16_t) + 64);
     if (!Lr) return SCTDA_ERR_NOMEM;
-    double* inv_q = (double*)sctda_ws(ctx, WS_MISC, (size_t)gr->V * sizeof(double) + 64 + (size_t)nlaunch * sizeof(unsigned long long));
-    if (!inv_q) return SCTDA_ERR_NOMEM;
-    int* unit_w = (int*)(inv_q + gr->V);
-    unsigned long long* counters = (unsigned long long*)(unit_w + 2);
-    const int one = 1;
+    // WS_MISC: inv_q | flags | queue heads | row headers | packed adjacency
+    const size_t off_flags = ((size_t)gr->V * sizeof(double) + 63) & ~(size_t)63;
+    const size_t off_counters = off_flags + 64;
+    const size_t off_rowinfo = (off_counters + (size_t)nlaunch * sizeof(unsigned long long) + 63) & ~(size_t)63;
+    const size_t off_ids = (off_rowinfo + (size_t)gr->V * sizeof(uint2) + 255) & ~(size_t)255;
+    size_t cap_chunks = 0;                                         // chunks of 8 ids the packed adjacency may take
+    if (gr->V <= 65535) {
+        cap_chunks = ((size_t)gr->V * ((size_t)gr->V + 1) / 2 + 7) / 8 + (size_t)gr->V;
+        if (cap_chunks > ((size_t)8 << 20)) cap_chunks = (size_t)8 << 20;   // 128 MB of ids at most
+    }
+    unsigned char* misc = (unsigned char*)sctda_ws(ctx, WS_MISC, off_ids + cap_chunks * 16 + 64);
+    if (!misc) return SCTDA_ERR_NOMEM;
+    double* inv_q = (double*)misc;
+    int* unit_w = (int*)(misc + off_flags);
+    int* packed_ok = unit_w + 1;
+    unsigned long long* counters = (unsigned long long*)(misc + off_counters);
+    uint2* rowinfo = (uint2*)(misc + off_rowinfo);
+    uint16_t* ids16 = (uint16_t*)(misc + off_ids);
+    const int ones[2] = {1, 1};
     SCTDA_CUDA(ctx, cudaMemsetAsync(counters, 0, (size_t)nlaunch * sizeof(unsigned long long), st));
-    SCTDA_CUDA(ctx, cudaMemcpyAsync(unit_w, &one, sizeof(int), cudaMemcpyHostToDevice, st));
-    unit_weight_wide_kernel<<<64, 256, 0, st>>>(gr->d_adj_off, gr->V, gr->d_adj_w, unit_w);
+    SCTDA_CUDA(ctx, cudaMemcpyAsync(unit_w, ones, sizeof(ones), cudaMemcpyHostToDevice, st));
+    unit_weight_wide_kernel<<<64, 256, 0, st>>>(gr->d_adj_off, gr->V, gr->d_adj_w, unit_w, (double*)(unit_w + 2));
     SCTDA_LAUNCH_CHECK(ctx, "unit_weight_wide_kernel");
+    if (cap_chunks) {
+        pack_adj_wide_kernel<<<1, 1024, 0, st>>>(gr->d_adj_off, gr->d_adj_idx, gr->V, (unsigned)cap_chunks, rowinfo, ids16, packed_ok);
+        SCTDA_LAUNCH_CHECK(ctx, "pack_adj_wide_kernel");
+    }
     gmap_wide_kernel<<<(tiles * kT + 255) / 256, 256, 0, st>>>(gmap, d_order, G, tiles * kT);
     SCTDA_LAUNCH_CHECK(ctx, "gmap_wide_kernel");
     if (Sp != gr->S) SCTDA_CUDA(ctx, cudaMemsetAsync(sec, 0, (size_t)tiles * Sp * sizeof(uint32_t), st));
@@ -617,7 +755,8 @@ int sctda_conn_perm_wide(sctda_ctx* ctx, const sctda_graph* gr, int G, const dou
     a.adj_off = gr->d_adj_off; a.adj_idx = gr->d_adj_idx; a.adj_w = gr->d_adj_w;
     a.ET = ET; a.sec = sec; a.Lr = Lr; a.gmap = gmap; a.inv_q = inv_q;
     a.observed = d_observed; a.tie_rel = tie_rel > 0.0 ? tie_rel : 1e-11;
-    a.exceed = d_exceed; a.ties = d_ties; a.scores = d_scores; a.unit_w = unit_w;
+    a.exceed = d_exceed; a.ties = d_ties; a.scores = d_scores; a.unit_w = unit_w; a.w0 = (const double*)(unit_w + 2);
+    a.rowinfo = cap_chunks ? rowinfo : nullptr; a.ids16 = ids16; a.packed_ok = packed_ok;
     const int NW = wide_warps();
     const size_t smem = wide_smem(Sp, NW);
     long long grid_max = ctx->sm_count;                            // one CTA per SM
