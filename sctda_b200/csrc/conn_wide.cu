@@ -24,7 +24,11 @@
 //     plus four DFMAs for 128 genes.
 //   * the log table is replicated eight times so that the 16-byte lookups of a quarter warp fall into eight
 //     different bank groups whatever the indices (4 wavefronts per lookup instead of ~9).
-// Tried and dropped (bit-identical, measured on the B200): rows stored COMPACTED to their non-empty sectors
+// Tried and dropped (bit-identical, measured on the B200, probe of 4,096 genes x 1,184 permutations = 112 ms):
+// `prefetch.global.L1` of the next gather round's sectors (144 ms: the prefetches queue in the same LSU pipe);
+// the next round's list entries read one round early (126 ms: spills at 80 registers); gather rounds of six or
+// eight members with 20 / 16 warps (125 / 131 ms); a table-free log (116 ms: six more FP64 instructions per node
+// value cost more than the 4 wavefronts of the lookup); rows stored COMPACTED to their non-empty sectors
 // (a lane's sector at popc(mask & lanes below)), so that the fetched sectors are contiguous.  The LSU data pipe
 // charges one wavefront per quad of lanes with an active lane, not per 128-byte line: wavefronts per
 // gene*permutation did not move (3,900 -> 3,900) and the extra offset lookups made the kernel 40 % slower.
@@ -154,7 +158,7 @@ __device__ __forceinline__ unsigned gather_one(double (&v)[kGPL], unsigned off, 
         "{\n.reg .pred p;\n.reg .b32 t;\n.reg .b64 ad;\n"
         "and.b32 t, %6, %7;\n setp.ne.u32 p, t, 0;\n"
         "mad.wide.u32 ad, %5, 32, %9;\n"
-        "@p ld.global.nc.L2::cache_hint.v4.f64 {%0, %1, %2, %3}, [ad], %8;\n"
+        "@p ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f64 {%0, %1, %2, %3}, [ad], %8;\n"   // a gathered row is used once
         "selp.b32 %4, 0x3ff00000, 0, p;\n}\n"
         : "+d"(v[0]), "+d"(v[1]), "+d"(v[2]), "+d"(v[3]), "=r"(mh)
         : "r"(off), "r"(mask), "r"(lanebit), "l"(pol), "l"(base));
@@ -666,7 +670,7 @@ static int wide_warps() {
     if (!nw) {
         const char* e = getenv("SCTDA_CONNW_WARPS");
         nw = e ? atoi(e) : 24;
-        if (nw < 8 || nw > 32 || nw % 4) nw = 24;
+        if (nw != 8 && nw != 16 && nw != 20 && nw != 24 && nw != 32) nw = 24;
     }
     return nw;
 }
@@ -776,10 +780,8 @@ int sctda_conn_perm_wide(sctda_ctx* ctx, const sctda_graph* gr, int G, const dou
         SCTDA_TIME_BEGIN(ctx, st);
         switch (NW) {
             case 8: rc = launch_wide<8>(ctx, a, grid, smem, st); break;
-            case 12: rc = launch_wide<12>(ctx, a, grid, smem, st); break;
             case 16: rc = launch_wide<16>(ctx, a, grid, smem, st); break;
             case 20: rc = launch_wide<20>(ctx, a, grid, smem, st); break;
-            case 28: rc = launch_wide<28>(ctx, a, grid, smem, st); break;
             case 32: rc = launch_wide<32>(ctx, a, grid, smem, st); break;
             default: rc = launch_wide<24>(ctx, a, grid, smem, st); break;
         }
