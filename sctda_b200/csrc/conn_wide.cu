@@ -28,7 +28,10 @@
 // `prefetch.global.L1` of the next gather round's sectors (144 ms: the prefetches queue in the same LSU pipe);
 // the next round's list entries read one round early (126 ms: spills at 80 registers); gather rounds of six or
 // eight members with 20 / 16 warps (125 / 131 ms); a table-free log (116 ms: six more FP64 instructions per node
-// value cost more than the 4 wavefronts of the lookup); rows stored COMPACTED to their non-empty sectors
+// value cost more than the 4 wavefronts of the lookup); two or three independent warp groups per CTA (named
+// barriers) working on different permutation chunks so that one group's adjacency phase (20 % of the time, LSU
+// pipe nearly idle) overlaps the others' gathers (+5 % / +35 % time: the phases share one L1/L2 path and the
+// smaller groups have fewer rows in flight); rows stored COMPACTED to their non-empty sectors
 // (a lane's sector at popc(mask & lanes below)), so that the fetched sectors are contiguous.  The LSU data pipe
 // charges one wavefront per quad of lanes with an active lane, not per 128-byte line: wavefronts per
 // gene*permutation did not move (3,900 -> 3,900) and the extra offset lookups made the kernel 40 % slower.
