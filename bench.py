@@ -25,6 +25,10 @@ a bounded sample of the same workload.
 EVERY N including 1 (cells/s; patches sharded over the ranks for N > 1), with the FP64
 contraction's roofline in both conventions (SURVEY 8d's algorithmic flops without symmetry
 credit, and the flops of the tiles actually executed); configs[1] (20k x 5k) rides along at N = 1.
+
+`rooted`: BASELINE.json configs[4] at every N: RootedGraph on a 50,000-cell Mapper graph through the
+reference-facing classes, the all-gene table (connectivity test + centroid / dispersion) with the genes
+sharded over the ranks.
 """
 import argparse
 import json
@@ -56,6 +60,7 @@ def parse():
     ap.add_argument('--nodes', type=int, default=2000)
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-mapper', action='store_true')
+    ap.add_argument('--no-rooted', action='store_true')
     ap.add_argument('--mapper-cells', type=int, default=20000)
     ap.add_argument('--mapper-genes', type=int, default=5000)
     ap.add_argument('--mapper-resolution', type=int, default=30)
@@ -423,6 +428,98 @@ def run_mapper(a, ctx, dev, steps, warmup, rank=0, world=1):
 # ---------------------------------------------------------------------------------------------
 # own arm
 # ---------------------------------------------------------------------------------------------
+def run_config5(a, ctx, dev, rank, world):
+    """BASELINE.json configs[4]: RootedGraph on a 50,000-cell Mapper graph through the reference-facing classes --
+    root finding (all-source BFS + Spearman scores on the device), root-distance pseudo-time regression, then the
+    connectivity test with the centroid / dispersion columns for every gene (RootedGraph.table, n = 500 shared
+    permutations), the genes sharded over the ranks inside UnrootedGraph.connectivity_pvalues.  Graph and table
+    are written once by rank 0 in the reference's formats (the table through the binary side-car)."""
+    import shutil
+    import tempfile
+    import torch
+    import torch.distributed as dist
+    from sctda_b200 import formats, graph, mapper, synth
+    N, G, n_perm, r, gain = 50000, 2000, 500, 30, 3.0
+    tmp = [None]
+    if rank == 0:
+        tmp[0] = tempfile.mkdtemp(prefix='sctda_c5_')
+    if world > 1:
+        dist.broadcast_object_list(tmp, src=0)
+    base = os.path.join(tmp[0], 'c5')
+    out = {'config': {'workload': 'RootedGraph on a %d-cell Mapper graph (euclidean, PCA lens, resolution %d, gain %g), '
+                                  '%d genes + time point column, %d shared permutations, genes sharded over %d B200'
+                                  % (N, r, gain, G, n_perm, world)}}
+    t, _ = synth._cell_latents(N, synth.SEED)
+    if rank == 0:
+        Yg = synth.expression_genes_torch(G, N, seed=synth.SEED, device=dev)          # gene-major [G, N]
+        X = Yg.t().contiguous()
+        lens = mapper.pca_lens_device(X).cpu().numpy()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        Gx, clusters, _ = mapper.mapper_graph(X.cpu().numpy(), lens, r, gain, metric='euclidean', verbose=False)
+        torch.cuda.synchronize()
+        out['mapper_graph_s'] = time.perf_counter() - t0
+        out['nodes'], out['edges'] = Gx.number_of_nodes(), Gx.number_of_edges()
+        formats.write_mapper_json(base + '_g.json', clusters)
+        formats.write_gexf(base + '_g.gexf', Gx.number_of_nodes(), sorted(Gx.edges()))
+        names = ['ID', 'timepoint', 'lib'] + ['G%05d' % i for i in range(G)]
+        with open(base + '.all.tsv', 'w') as f:
+            f.write('\t'.join(names) + '\n')
+        tp = numpy.floor(t * 5.0)
+        Y = numpy.empty((len(names), N), dtype=numpy.float64)
+        Y[0] = 0.0
+        Y[1] = tp
+        Y[2] = 0.0
+        Y[3:] = Yg.cpu().numpy()
+        cdr = (Y[3:] > 0).sum(axis=0) / float(G)
+        formats.write_table_sidecar(base + '.all.tsv', names, Y, ['D%d_%d' % (int(tp[i]), i) for i in range(N)],
+                                    ['L'] * N, cdr)
+        del Y, Yg, X
+        torch.cuda.empty_cache()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    c = graph.RootedGraph(base + '_g', base + '.all.tsv', groups=False, device=dev.index)
+    torch.cuda.synchronize()
+    init_s = time.perf_counter() - t0
+    dg = c._device_graph()
+    perms = synth.permutation_block_torch(n_perm, int(dg.S), seed=7, device=dev).cpu().numpy()
+    c.table(n=n_perm, perms=perms)                                                    # warm-up (workspaces, stats)
+    times = []
+    for _ in range(3):
+        c._stats = None
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        header, rows = c.table(n=n_perm, perms=perms)
+        torch.cuda.synchronize()
+        times.append(time.perf_counter() - t0)
+    tt = torch.tensor([float(numpy.median(times)), init_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    table_s, init_max = float(tt[0].item()), float(tt[1].item())
+    cen = numpy.array([row[8] for row in rows if row[8] is not None], dtype=numpy.float64)
+    out.update({'metric': 'RootedGraph all-gene table: gene*perms/s', 'value': len(rows) * n_perm / table_s,
+                'unit': 'gene*perms/s', 'n_gpus': world, 'table_s': table_s, 'table_s_runs': [round(x, 4) for x in times],
+                'rooted_init_s': init_max, 'rows': len(rows), 'nodes_lcc': len(c.pl), 'cells_lcc': int(dg.S),
+                'memberships': int(dg.Mtot), 'root': str(c.root), 'leaf': str(c.leaf),
+                'skeleton': {'levels': len(c.dicdend), 'nodes': c.g3.number_of_nodes(), 'edges': c.g3.number_of_edges(),
+                             'path_edges': len(c.select_diff_path())},
+                'pseudotime_regression': {'slope': float(c.po[0]), 'intercept': float(c.po[1]), 'r': float(c.po[2])},
+                'centroid_range': [float(cen.min()), float(cen.max())] if cen.size else None,
+                'significant_q05': int(sum(1 for row in rows if row[7] <= 0.05)),
+                'includes': 'node statistics of every table column (get_gene / delta / expr / connectivity / centroid sums), '
+                            'the permutation test of the kept genes (genes sharded, counts all-gathered), BH, the rows; '
+                            'rooted_init_s (untimed in value): files -> graph, all-source BFS + Spearman root scores, '
+                            'skeleton, regression'})
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        shutil.rmtree(tmp[0], ignore_errors=True)
+    return out
+
+
 def run_own(a):
     import torch
     import torch.distributed as dist
@@ -563,7 +660,7 @@ def run_own(a):
             'note': 'permutation block shared by all genes: index traffic is amortised over the gene shard; the kernel gathers '
                     'only the 32-byte sectors of the transposed table that hold a non-zero (sector_density x 8*Mtot bytes per '
                     'gene*perm from L2) and is bound by the bytes it can keep in flight (register landing zone x L2 latency) '
-                    'and by the LSU data pipe (one wavefront per touched 128-byte line; DESIGN.md)'}
+                    'and by the LSU data pipe (one wavefront per quad of lanes with an active lane; DESIGN.md)'}
 
     mapper_line = None
     if not a.no_mapper:
@@ -575,6 +672,10 @@ def run_own(a):
         mapper_line = run_mapper(a, ctx, dev, 5, 2, rank, world)    # 5 timed builds, median reported
         if rank == 0 and world == 1 and not a.no_cpu:
             mapper_line['cpu_baseline'] = mapper_cpu_sample()
+    rooted_line = None
+    if not a.no_rooted:
+        torch.cuda.empty_cache()
+        rooted_line = run_config5(a, ctx, dev, rank, world)
     if rank == 0:
         cpu = None
         if world == 1 and not a.no_cpu:
@@ -591,7 +692,8 @@ def run_own(a):
                 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': workload_config(a, world),
                 'clocks': clocks.summary(), 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roof,
                 'cpu_baseline': cpu, 'plan_ms_untimed': plan_ms,
-                'degenerate_genes_with_exact_ties': int((ties > 0).sum().item()), 'mapper': mapper_line}
+                'degenerate_genes_with_exact_ties': int((ties > 0).sum().item()), 'mapper': mapper_line,
+                'rooted': rooted_line}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

@@ -25,6 +25,8 @@ Shim (everything that differs from running the file under Python 2):
   S8  numpy.infty                     -> numpy.inf               (textual; attribute removed in numpy 2)
   S9  dict.values() inside numpy.array -> list(dict.values())    (textual, ref:1118 only; a Py2 dict.values()
                                                                    is a list)
+  S10 sch.dendrogram                  -> called with no_plot=True (matplotlib is not installed; the returned
+                                         record does not depend on the plot)
 
 Run:  python oracle/gen_golden.py          (rewrites tests/golden/)
 """
@@ -166,6 +168,17 @@ def load_reference():
     mod.networkx = _NetworkxProxy()
     mod.numexpr = ne
     mod.pickle = pk
+    import scipy.cluster.hierarchy as real_sch
+
+    class _Sch(object):                                                          # S10
+        def __getattr__(self, name):
+            return getattr(real_sch, name)
+
+        @staticmethod
+        def dendrogram(*a, **k):
+            k['no_plot'] = True
+            return real_sch.dendrogram(*a, **k)
+    mod.sch = _Sch()
     return mod
 
 
@@ -224,6 +237,10 @@ def write_case(prefix, n_cells, n_genes, n_nodes, seed, extra_component=True):
     with open(prefix + '.json', 'w') as f:
         json.dump(dic, f)
     networkx.write_gexf(g, prefix + '.gexf')
+    with open(prefix + '.gexf') as f:                                            # keep the file independent of the day it is made
+        txt = re.sub(r'lastmodifieddate="[^"]*"', 'lastmodifieddate="2026-10-19"', f.read())
+    with open(prefix + '.gexf', 'w') as f:
+        f.write(txt)
     return genes
 
 
@@ -281,9 +298,27 @@ def run_case(ref, prefix, n_perm, seed, rooted):
             'adjacency': [[float(v) for v in row] for row in c.adjacency_matrix(lista)],
             'adjacency_2': [[float(v) for v in row] for row in c.adjacency_matrix(lista, ind=2)],
         }
+    if rooted:
+        # the skeleton of ref:1499-1556 and the path of ref:1569-1593
+        out['skeleton'] = {
+            'nodes': [str(x) for x in c.g3.nodes()],
+            'edges': [[str(a), str(b)] for a, b in c.g3.edges()],
+            'dicdend': {str(n): [sorted(str(x) for x in comp) for comp in comps] for n, comps in c.dicdend.items()},
+            'edgesize': [int(x) for x in c.edgesize],
+            'nodesize': [int(x) for x in c.nodesize],
+            'select_diff_path': [[str(a), str(b)] for a, b in c.select_diff_path()],
+        }
     # the table writer, RNG stream consumed gene by gene from `seed`
     numpy.random.seed(seed)
     c.save(n=n_perm, filtercells=0, filterexp=0.0, annotation={'setA': genes[3:9], 'setB': genes[5:6]})
+    # ref:1423-1446 on the table just written (every gene expressed in more than 5 cells: the q-value bound is
+    # lifted so that the small case has genes to cluster)
+    with numpy.errstate(invalid='ignore', divide='ignore'):
+        if rooted:                                                               # ref:1950-2040, the 'js' route
+            cl = c.cellular_subpopulations(1e9, threshold=1.5, min_cells=5, method='js', clus_thres=0.65)
+        else:
+            cl = c.cellular_subpopulations(threshold=1.5, min_cells=5, clus_thres=0.65)
+        out['cellular_subpopulations'] = {'threshold': 1.5, 'min_cells': 5, 'clus_thres': 0.65, 'clusters': cl}
     os.replace(prefix + '.genes.tsv', prefix + '.ref.genes.tsv')
     with open(prefix + '.ref.json', 'w') as f:
         json.dump(out, f)
@@ -305,6 +340,9 @@ def main():
         prefix = os.path.join(GOLD, name)
         write_case(prefix, **kw)
         run_case(ref, prefix, n_perm, seed, rooted)
+        for ext in ('.posg', '.posgl', '.genes.tsv'):                            # by-products of the reference's constructor
+            if os.path.exists(prefix + ext):
+                os.remove(prefix + ext)
         print('golden case', name, 'written')
 
 

@@ -40,6 +40,44 @@ def benjamini_hochberg(pvalues):
     return list(out)
 
 
+def hierarchical_clustering(mat, method='average', cluster_distance=True, labels=None, thres=0.65):
+    """ref:204-255 without the figure: linkage (`method`) of the rows of `mat` under the euclidean
+    distance (cluster_distance=True) or of `mat` itself taken as a distance matrix; returns the
+    dendrogram record scipy colours at `thres` times the largest merge height (what find_clusters
+    reads).  `labels` only annotated the reference's figure.  scipy's linkage / dendrogram are the
+    reference's own calls; cellular_subpopulations computes the row distances on the device."""
+    return _hierarchical_clustering(mat, method, cluster_distance, thres, None)
+
+
+def _hierarchical_clustering(mat, method, cluster_distance, thres, ctx):
+    import scipy.cluster.hierarchy as sch
+    import scipy.spatial.distance
+    D = numpy.array(mat, dtype=numpy.float64)
+    if not cluster_distance:
+        tri = scipy.spatial.distance.squareform(D)                              # ref:215
+    elif ctx is not None and D.shape[0] > 1:
+        from . import mapper
+        dev = torch.device('cuda', ctx.device)
+        full = mapper.pairwise_distances(ctx, mapper._padded_device_table(torch.from_numpy(D).to(dev), dev),
+                                         'euclidean').cpu().numpy()
+        tri = full[numpy.triu_indices(D.shape[0], k=1)]                         # pdist order, ref:217
+    else:
+        tri = scipy.spatial.distance.pdist(D, metric='euclidean')
+    Y = sch.linkage(tri, method=method)                                         # ref:220
+    return sch.dendrogram(Y, orientation='right', color_threshold=thres * max(Y[:, 2]), no_plot=True)
+
+
+def find_clusters(z):
+    """ref:258-266: leaves of the dendrogram record `z` grouped by the colour of the link they hang from
+    (all leaves that join above the colour threshold share the default colour, hence one group)."""
+    clus = {}
+    for colour, xs, ys in zip(z['color_list'], z['icoord'], z['dcoord']):
+        for x, y in zip(xs, ys):
+            if y == 0.0:                                                         # a leaf end of the link
+                clus.setdefault(colour, []).append(z['leaves'][int((x - 5.0) / 10.0)])
+    return clus
+
+
 def reference_perm_indices(n, S, rng=None):
     """The permutation source of ref:975-976 as index arrays: row r of an n x S block is
     arange(S) shuffled by numpy.random.shuffle, rows in order, from the GLOBAL legacy
@@ -426,8 +464,20 @@ class UnrootedGraph(object):
                 raise ValueError('perms has %d rows but n = %d: pass n = perms.shape[0] (the p-value is the exceed '
                                  'count over the number of permutations applied)' % (perms.shape[0], n))
             pd = torch.as_tensor(numpy.ascontiguousarray(perms, dtype=numpy.int32)).to(dev)
-            Ysel = Yd.index_select(0, self._rows(genes))
-            ex, ti, _ = conn_perm_test(ctx, dg, Ysel, pd, obs_all, log2=self.log2, gene_order=geneorder.gene_order(Ysel))
+            from . import parallel
+            rank, ws = parallel.world()
+            # under torch.distributed the genes are sharded over the ranks (contiguous shards, no collective on
+            # the data path) and the counts gathered on every rank
+            lo, hi = parallel.shard_range(len(genes), rank, ws) if ws > 1 else (0, len(genes))
+            if hi > lo:
+                Ysel = Yd.index_select(0, self._rows(genes[lo:hi]))
+                ex, ti, _ = conn_perm_test(ctx, dg, Ysel, pd, obs_all[lo:hi], log2=self.log2,
+                                           gene_order=geneorder.gene_order(Ysel))
+            else:
+                ex = ti = torch.zeros(0, dtype=torch.int32, device=dev)
+            if ws > 1:
+                ex = torch.cat(parallel.all_gather_varlen(ex.to(torch.int32).reshape(-1)))
+                ti = torch.cat(parallel.all_gather_varlen(ti.to(torch.int32).reshape(-1)))
             pvals = ex.cpu().numpy() / float(n)
             ties = ti.cpu().numpy()
         else:
@@ -482,6 +532,22 @@ class UnrootedGraph(object):
         cor = float(V) / float(V - 1)
         return (cor * M).cpu().numpy()
 
+    def cellular_subpopulations(self, threshold=0.05, min_cells=5, clus_thres=0.65):
+        """ref:1423-1446: genes of name.genes.tsv with q-value below `threshold` expressed in more than
+        `min_cells` cells, clustered by average linkage on the rows of their Jensen-Shannon distance
+        matrix (device: sctda_jsd_matrix, then the row distances by the FP64 contraction); returns the
+        list of gene lists, one per dendrogram colour at `clus_thres`."""
+        nam = []
+        with open(self.name + '.genes.tsv', 'r') as f:
+            for n, line in enumerate(f):
+                if n > 0:
+                    sp = line[:-1].split('\t')
+                    if float(sp[7]) < threshold and float(sp[1]) > min_cells:
+                        nam.append(sp[0])
+        mat2 = self.JSD_matrix(nam)
+        z = _hierarchical_clustering(mat2, 'average', True, clus_thres, self._context())
+        return [[nam[x] for x in m] for m in find_clusters(z).values()]
+
     # -- table (ref:1053-1086) -----------------------------------------------------------------------
     def _table_rows(self, n, filtercells, filterexp, annotation, rooted, perms):
         s = self._all_stats()
@@ -529,6 +595,7 @@ class RootedGraph(UnrootedGraph):
         self.rootlane = rootlane
         self.root, self.leaf = self.find_root(self.get_dendrite())               # ref:1536
         self.dicdis = self.get_distroot(self.root)                               # ref:1562
+        self._skeleton_state()                                                   # ref:1537-1556
         pel2, tol = self.get_gene(self.rootlane, ignore_log=True)                # ref:1563
         pel = numpy.array([pel2[m] for m in self.pl]) * tol
         dr = numpy.array([self.dicdis[m] for m in self.pl])
@@ -591,6 +658,121 @@ class RootedGraph(UnrootedGraph):
         root = keys[int(numpy.argmin(lo))] if numpy.isfinite(lo).any() else 0
         leaf = keys[int(numpy.argmax(hi))] if numpy.isfinite(hi).any() else 0
         return root, leaf
+
+    def dendritic_graph(self):
+        """ref:1499-1520: skeleton of the graph.  Level n = the nodes of the largest component at hop
+        distance n from the root (n < diameter - 1; distances and eccentricities from the device BFS of
+        sctda_root_scores); dicdend[n] = connected components of the level (ordered by their first node in
+        self.pl order, the order networkx yields them in); skeleton nodes 'n_i', an edge between
+        components of consecutive levels whose union is connected."""
+        import scipy.sparse.csgraph
+        dist_all = self._root_scores()[1]
+        diam = int(dist_all.max())
+        d = numpy.array([self.dicdis[k] for k in self.pl])
+        A = scipy.sparse.csr_matrix(((self.adj_csr + self.adj_csr.T) != 0).astype(numpy.int8))
+        g3 = networkx.Graph()
+        dicdend = {}
+        comp_of = {}
+        for n in range(diam - 1):
+            idx = numpy.nonzero(d == n)[0]
+            comps = []
+            if idx.size:
+                ncomp, lab = scipy.sparse.csgraph.connected_components(A[idx][:, idx], directed=False)
+                order = []
+                for c in lab:                                                    # components by first appearance
+                    if c not in order:
+                        order.append(int(c))
+                comps = [set(self.pl[i] for i in idx[lab == c]) for c in order]
+                for n2, c in enumerate(order):
+                    comp_of[(n, n2)] = idx[lab == c]
+            dicdend[n] = comps
+            for n2 in range(len(comps)):
+                g3.add_node('%d_%d' % (n, n2))
+                if n > 0:
+                    for n3 in range(len(dicdend[n - 1])):
+                        # both parts are connected: the union is connected iff an edge joins them
+                        if A[comp_of[(n, n2)]][:, comp_of[(n - 1, n3)]].nnz > 0:
+                            g3.add_edge('%d_%d' % (n, n2), '%d_%d' % (n - 1, n3))
+        self._comp_idx = comp_of
+        self._sym = A
+        return g3, dicdend
+
+    def _skeleton_state(self):
+        """ref:1537-1556: sizes of the skeleton's edges (graph edges between the two components) and nodes
+        (distinct cells of a component)."""
+        self.g3, self.dicdend = self.dendritic_graph()
+        self.edgesize, self.dicedgesize = [], {}
+        self.nodesize, self.dicmelisa = [], {}
+        self.edgesizeprun, self.nodesizeprun, self.dicmelisaprun = [], [], {}
+        key = lambda name: tuple(int(x) for x in name.split('_'))
+        for ee in self.g3.edges():
+            a, b = self._comp_idx[key(ee[0])], self._comp_idx[key(ee[1])]
+            self.edgesize.append(int(self._sym[a][:, b].nnz))
+            self.dicedgesize[ee] = self.edgesize[-1]
+        for ee in self.g3.nodes():
+            cells = set()
+            for uu in self.dicdend[key(ee)[0]][key(ee)[1]]:
+                cells.update(self.dic[uu])
+            self.nodesize.append(len(cells))
+            self.dicmelisa[ee] = cells
+
+    def select_diff_path(self):
+        """ref:1569-1593: the path through the skeleton that starts at '0_0' and always follows the
+        heaviest unused edge towards a deeper level (the first such edge in dictionary order on ties)."""
+        level = lambda name: int(name.split('_')[0])
+        lista, last = [], '0_0'
+        while True:
+            best, siz = None, 0
+            for ee, sz in self.dicedgesize.items():
+                down = (ee[0] == last and level(ee[1]) > level(ee[0])) or (ee[1] == last and level(ee[0]) > level(ee[1]))
+                if down and sz > siz and ee not in lista:
+                    best, siz = ee, sz
+            if best is None:
+                return lista
+            lista.append(best)
+            last = best[1] if level(best[1]) > level(best[0]) else best[0]
+
+    def cellular_subpopulations(self, min_dispersion, threshold=0.05, min_cells=5, max_K=8, method='centroid',
+                                clus_thres=0.65):
+        """ref:1950-2040.  method='js': the Jensen-Shannon route of UnrootedGraph.cellular_subpopulations.
+        method='centroid': genes of name.genes.tsv with dispersion below `min_dispersion`, q-value below
+        `threshold`, expressed in more than `min_cells` cells; their centroids are cut by k-means for
+        k = 2 .. max_K - 1 (sklearn KMeans, random_state=170, as the reference) and the k with the smallest mean
+        of max_j (var_i - var_j) / |mean_i - mean_j| is kept (the reference's own variant of the Davies-Bouldin
+        index, ref:1995-2003); returns the gene lists of the clusters.  The two figures are not drawn."""
+        if method == 'js':
+            return UnrootedGraph.cellular_subpopulations(self, threshold=threshold, min_cells=min_cells,
+                                                         clus_thres=clus_thres)
+        if method != 'centroid':
+            return None                                                          # the reference falls through
+        import sklearn.cluster
+        con, nam = [], []
+        with open(self.name + '.genes.tsv', 'r') as f:
+            for n, line in enumerate(f):
+                if n > 0:
+                    sp = line[:-1].split('\t')
+                    if float(sp[9]) < min_dispersion and float(sp[7]) < threshold and float(sp[1]) > min_cells:
+                        con.append(float(sp[8]))
+                        nam.append(sp[0])
+        pts = numpy.array([[c, 0.0] for c in con])
+
+        def labels(m):
+            return sklearn.cluster.KMeans(n_clusters=m, random_state=170).fit_predict(pts)
+        y = []
+        for m in range(2, max_K):
+            pred = labels(m)
+            clus = [[q for t, q in zip(pred, con) if t == i] for i in range(m)]
+            var = [numpy.var(c) for c in clus]
+            mean = [numpy.mean(c) for c in clus]
+            ri = [max([0.0 if j == i else (var[i] - var[j]) / abs(mean[i] - mean[j]) for j in range(m)]) for i in range(m)]
+            y.append(numpy.mean(ri))
+        vals = numpy.array(y, dtype=numpy.float64)
+        ok = vals < numpy.inf                                                    # NaN and inf never win the `<` of ref:2016-2021
+        rn = int(numpy.argmin(numpy.where(ok, vals, numpy.inf))) if ok.any() else -1   # first minimum
+        g = [[] for _ in range(rn + 2)]
+        for m, n in zip(list(labels(rn + 2)), nam):
+            g[m].append(n)
+        return g
 
     def _centroid_from_raw(self, cen, disp):
         if numpy.isnan(cen):

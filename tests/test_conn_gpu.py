@@ -375,6 +375,47 @@ def test_gene_gene_matrices_match_reference_golden(golden_dir, tmp_path, name):
     numpy.testing.assert_allclose(c.adjacency_matrix(genes, ind=2), numpy.array(ref['adjacency_2']), rtol=1e-11, atol=0)
 
 
+@pytest.mark.parametrize('name', ['unrooted_a', 'rooted_b'])
+def test_skeleton_and_subpopulations_match_reference_golden(golden_dir, tmp_path, name):
+    """cellular_subpopulations (ref:1423-1446, 1950-2040 'js' route) on the gene table the reference wrote, and the
+    skeleton of RootedGraph (dendritic_graph, edge / node sizes, select_diff_path: ref:1499-1593), against what the
+    reference's own methods returned on these files (oracle/gen_golden.py)."""
+    _gpu()
+    from sctda_b200 import graph
+    for ext in ('.gexf', '.json', '.all.tsv'):
+        shutil.copy(os.path.join(golden_dir, name + ext), str(tmp_path / (name + ext)))
+    shutil.copy(os.path.join(golden_dir, name + '.ref.genes.tsv'), str(tmp_path / (name + '.genes.tsv')))
+    with open(os.path.join(golden_dir, name + '.ref.json')) as f:
+        ref = json.load(f)
+    prefix = str(tmp_path / name)
+    r = ref['cellular_subpopulations']
+    if ref['rooted']:
+        c = graph.RootedGraph(prefix, prefix + '.all.tsv', groups=False)
+        got = c.cellular_subpopulations(1e9, threshold=r['threshold'], min_cells=r['min_cells'], method='js',
+                                        clus_thres=r['clus_thres'])
+        k = ref['skeleton']
+        assert [str(x) for x in c.g3.nodes()] == k['nodes']
+        assert [[str(a), str(b)] for a, b in c.g3.edges()] == k['edges']
+        assert {str(n): [sorted(comp) for comp in comps] for n, comps in c.dicdend.items()} == k['dicdend']
+        assert c.edgesize == k['edgesize'] and c.nodesize == k['nodesize']
+        assert [[a, b] for a, b in c.select_diff_path()] == k['select_diff_path']
+        # the centroid route: two planted groups of centroids come back as the two clusters
+        rows = ['\t'.join(['Gene', 'Cells', 'Mean', 'Min', 'Max', 'Connectivity', 'p_value', 'q-value (BH)', 'Centroid',
+                           'Dispersion'])]
+        rs = numpy.random.RandomState(4)
+        for i in range(40):
+            cen = (0.2 if i < 25 else 0.8) + 0.01 * rs.randn()
+            rows.append('\t'.join(['g%02d' % i, '50', '1', '0', '2', '0.5', '0.001', '0.01', repr(float(cen)), '0.1']))
+        with open(prefix + '.genes.tsv', 'w') as f:
+            f.write('\n'.join(rows) + '\n')
+        groups = c.cellular_subpopulations(0.5, max_K=5)
+        assert sorted(sorted(g) for g in groups) == [['g%02d' % i for i in range(25)], ['g%02d' % i for i in range(25, 40)]]
+    else:
+        c = graph.UnrootedGraph(prefix, prefix + '.all.tsv', groups=False)
+        got = c.cellular_subpopulations(threshold=r['threshold'], min_cells=r['min_cells'], clus_thres=r['clus_thres'])
+    assert got == r['clusters']
+
+
 @pytest.mark.parametrize('n_cells', [30000, 60000])
 def test_large_components_use_the_other_staging_paths(n_cells):
     """S = 30,000: the permutation row is staged in shared memory without double buffering;

@@ -333,3 +333,26 @@ def test_native_formatter_fuzz():
     rows = formats.format_rows(v)
     for r in range(v.shape[0]):
         assert rows[r].decode() == '\t'.join(formats.py2_str(x) for x in v[r])
+
+
+def test_hierarchical_clustering_and_find_clusters():
+    """ref:204-266 without the figure: the colour groups partition the leaves; every group but the
+    default-colour one is a flat cluster of scipy's fcluster at the same height."""
+    import scipy.cluster.hierarchy as sch
+    import scipy.spatial.distance
+    from sctda_b200 import graph
+    rs = numpy.random.RandomState(2)
+    pts = numpy.concatenate([rs.randn(6, 3) + 8.0, rs.randn(5, 3) - 8.0, 40.0 * rs.randn(3, 3)])
+    mat = scipy.spatial.distance.squareform(scipy.spatial.distance.pdist(pts))
+    for cluster_distance in (True, False):
+        z = graph.hierarchical_clustering(mat, cluster_distance=cluster_distance, thres=0.3)
+        groups = graph.find_clusters(z)
+        leaves = sorted(x for g in groups.values() for x in g)
+        assert leaves == list(range(len(pts)))
+        tri = scipy.spatial.distance.pdist(mat) if cluster_distance else scipy.spatial.distance.squareform(mat)
+        Y = sch.linkage(tri, method='average')
+        flat = sch.fcluster(Y, 0.3 * Y[:, 2].max(), 'distance')
+        big = sorted(sorted(numpy.nonzero(flat == f)[0].tolist()) for f in set(flat) if (flat == f).sum() > 1)
+        mine = sorted(sorted(g) for g in groups.values())
+        for b in big:
+            assert b in mine

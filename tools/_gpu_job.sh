@@ -1,9 +1,3 @@
 set -x
-P="python tools/conn_probe.py --genes 1024 --perms 4736 --order pca --reps 2"
-SCTDA_CONNW_GROUPS=1 $P
-SCTDA_CONNW_GROUPS=2 $P
-SCTDA_CONNW_GROUPS=2 SCTDA_CONNW_STAGGER_US=400 $P
-SCTDA_CONNW_GROUPS=3 $P
-SCTDA_CONNW_GROUPS=3 SCTDA_CONNW_STAGGER_US=300 $P
-SCTDA_CONNW_GROUPS=2 SCTDA_CONNW_WARPS=20 $P
-SCTDA_CONNW_GROUPS=2 SCTDA_CONNW_WARPS=16 $P
+python -m pytest tests -m gpu -x -q 2>&1 | tail -8
+python bench.py --steps 3 --warmup 3 > gpurun_out/bench_s2.json 2> gpurun_out/bench_s2.err; tail -c 2500 gpurun_out/bench_s2.json; tail -5 gpurun_out/bench_s2.err
