@@ -58,12 +58,22 @@ def gene_sharded_counts(n_genes, compute):
     return torch.cat(all_gather_varlen(mine))
 
 
-def assign_patches_lpt(sizes, world_size):
-    """Deal patches to ranks by descending m^2 (the Gram tile and the MST are O(m^2)), each to the
-    currently least loaded rank.  Deterministic.  Returns a list of ascending patch-index arrays."""
+# Cost model of the patch dealer, in units of one entry of a patch Gram tile (measured on a B200, 100k x 2k build,
+# tools/lpt_probe.py: 7.4e-8 ms per entry for the contraction; 2.4e-3 ms per dependent step of the MST of a patch
+# above CHAIN_MIN cells).  The MSTs of a rank's large patches run side by side, one cluster of CTAs each, after the
+# contraction: a rank pays the chain of its LARGEST patch once, on top of its tiles.
+CHAIN_MIN = 4096
+CHAIN_ENTRIES_PER_STEP = 3.2e4
+
+
+def assign_patches_lpt(sizes, world_size, chain=True):
+    """Deal patches to ranks by descending size, each to the currently least loaded rank; load = the m^2 entries of
+    the rank's Gram tiles plus the MST chain of its largest patch (the first one it is dealt).  Deterministic.
+    Returns a list of ascending patch-index arrays."""
     sizes = numpy.asarray(sizes, dtype=numpy.int64)
     order = numpy.lexsort((numpy.arange(sizes.size), -sizes))        # descending size, ties by index
     load = numpy.zeros(world_size, dtype=numpy.float64)
+    fresh = numpy.ones(world_size, dtype=bool)
     owner = numpy.full(sizes.size, -1, dtype=numpy.int64)
     for b in order:
         if sizes[b] == 0:
@@ -72,6 +82,9 @@ def assign_patches_lpt(sizes, world_size):
         r = int(numpy.argmin(load))
         owner[b] = r
         load[r] += float(sizes[b]) ** 2
+        if chain and fresh[r] and sizes[b] > CHAIN_MIN:
+            load[r] += CHAIN_ENTRIES_PER_STEP * float(sizes[b])
+        fresh[r] = False
     return [numpy.nonzero(owner == r)[0] for r in range(world_size)]
 
 
