@@ -466,18 +466,37 @@ class UnrootedGraph(object):
             pd = torch.as_tensor(numpy.ascontiguousarray(perms, dtype=numpy.int32)).to(dev)
             from . import parallel
             rank, ws = parallel.world()
-            # under torch.distributed the genes are sharded over the ranks (contiguous shards, no collective on
-            # the data path) and the counts gathered on every rank
-            lo, hi = parallel.shard_range(len(genes), rank, ws) if ws > 1 else (0, len(genes))
-            if hi > lo:
-                Ysel = Yd.index_select(0, self._rows(genes[lo:hi]))
-                ex, ti, _ = conn_perm_test(ctx, dg, Ysel, pd, obs_all[lo:hi], log2=self.log2,
-                                           gene_order=geneorder.gene_order(Ysel))
-            else:
-                ex = ti = torch.zeros(0, dtype=torch.int32, device=dev)
+            rows_all = self._rows(genes)
             if ws > 1:
+                # under torch.distributed the genes are sharded over the ranks (no collective on the data path)
+                # and the counts gathered on every rank.  The tile plan is made on ALL the genes
+                # (rank 0, broadcast: every rank must cut the same shards) and a rank takes every N-th 128-gene tile
+                # of the planned order: tiles as homogeneous as on one GPU, the same mix of sparse and dense tiles
+                # on every rank.
+                import torch.distributed as dist
+                plan = geneorder.gene_order(Yd.index_select(0, rows_all)).long() if rank == 0 else \
+                    torch.empty(len(genes), dtype=torch.int64, device=dev)
+                if dist.get_backend() == 'nccl':
+                    dist.broadcast(plan, src=0)
+                else:
+                    pc = plan.cpu()
+                    dist.broadcast(pc, src=0)
+                    plan = pc.to(dev)
+                pos = [torch.from_numpy(parallel.tile_shard_positions(len(genes), r, ws)).to(dev) for r in range(ws)]
+                mine = plan.index_select(0, pos[rank])
+                if mine.numel() > 0:
+                    ex, ti, _ = conn_perm_test(ctx, dg, Yd.index_select(0, rows_all.index_select(0, mine)), pd,
+                                               obs_all.index_select(0, mine), log2=self.log2)
+                else:
+                    ex = ti = torch.zeros(0, dtype=torch.int32, device=dev)
                 ex = torch.cat(parallel.all_gather_varlen(ex.to(torch.int32).reshape(-1)))
                 ti = torch.cat(parallel.all_gather_varlen(ti.to(torch.int32).reshape(-1)))
+                back = plan.index_select(0, torch.cat(pos))                 # gathered slot -> position in `genes`
+                ex = torch.empty_like(ex).index_copy_(0, back, ex)
+                ti = torch.empty_like(ti).index_copy_(0, back, ti)
+            else:
+                Ysel = Yd.index_select(0, rows_all)
+                ex, ti, _ = conn_perm_test(ctx, dg, Ysel, pd, obs_all, log2=self.log2, gene_order=geneorder.gene_order(Ysel))
             pvals = ex.cpu().numpy() / float(n)
             ties = ti.cpu().numpy()
         else:

@@ -25,6 +25,15 @@ def shard_range(n, rank, world_size):
     return (n * rank) // world_size, (n * (rank + 1)) // world_size
 
 
+def tile_shard_positions(n, rank, world_size, tile=128):
+    """Positions (ascending) of a planned gene order that `rank` works on: the 128-gene tiles of the order are
+    dealt round-robin, so that every rank gets the same mix of sparse and dense tiles (a contiguous range of the
+    order would hand one rank all the dense genes) while each tile stays as homogeneous as the plan made it."""
+    import numpy
+    pos = numpy.arange(n, dtype=numpy.int64)
+    return pos[(pos // tile) % world_size == rank]
+
+
 def _comm_device():
     return torch.device('cuda', torch.cuda.current_device()) if dist.get_backend() == 'nccl' else torch.device('cpu')
 

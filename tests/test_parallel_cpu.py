@@ -158,3 +158,19 @@ def test_patch_shard_plan_places_every_fragment(ws):
         labels[bin_off[b]:bin_off[b + 1]] = gathered[owner[b], frag_off[b]:frag_off[b] + sizes[b]]
         K[b] = gathered_K[owner[b], frag_idx[b]]
     assert (labels == truth).all() and (K == truth_K).all()
+
+
+def test_tile_shard_positions_partition_the_planned_order():
+    """Every position of the planned gene order belongs to exactly one rank; whole 128-gene tiles stay together and
+    are dealt round-robin."""
+    from sctda_b200 import parallel
+    for n in (0, 1, 127, 128, 129, 1000, 20000):
+        for ws in (1, 2, 3, 8):
+            parts = [parallel.tile_shard_positions(n, r, ws) for r in range(ws)]
+            allpos = numpy.sort(numpy.concatenate(parts)) if n else numpy.zeros(0, dtype=numpy.int64)
+            assert allpos.tolist() == list(range(n))
+            for r, p in enumerate(parts):
+                assert ((p // 128) % ws == r).all()
+                assert (numpy.diff(p) > 0).all()
+            sizes = [p.size for p in parts]
+            assert max(sizes) - min(sizes) <= 128

@@ -1,3 +1,2 @@
-python tools/lpt_probe.py 8 2>&1 | tail -19
-python tools/lpt_probe.py 4 2>&1 | grep slowest
-python tools/lpt_probe.py 2 2>&1 | grep slowest
+set -x
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29541 bench.py --gpus 8 --steps 3 --warmup 3 > gpurun_out/bench_n8c.json 2> gpurun_out/bench_n8c.err; tail -c 300 gpurun_out/bench_n8c.json; tail -3 gpurun_out/bench_n8c.err

@@ -44,7 +44,8 @@ def main():
     if a.order != 'none':
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        order = geneorder.gene_order(Y, method=a.order)
+        kw = {k: int(os.environ[e]) for k, e in (('sample', 'GO_SAMPLE'), ('dims', 'GO_DIMS'), ('leaf', 'GO_LEAF')) if e in os.environ}
+        order = geneorder.gene_order(Y, method=a.order, **kw)
         torch.cuda.synchronize()
         t_order = time.perf_counter() - t0
     ms = []
