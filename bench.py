@@ -298,10 +298,10 @@ def fp64_probe_tflops(dev):
     return best
 
 
-def executed_tile_flops(sizes, G, tile=128):
-    """Flops of the 128 x 128 output tiles gemm_kernel executes for symmetric patch Gram matrices: the upper
-    triangle of tiles only (T(T+1)/2 tiles of a patch of ceil(m/128) = T tile rows), every tile counted
-    in full (edge tiles compute their padding)."""
+def executed_tile_flops(sizes, G, tile):
+    """Flops of the tile x tile output tiles gemm_kernel executes for symmetric patch Gram matrices (tile =
+    sctda_gemm_tile_fp64()): the upper triangle of tiles only (T(T+1)/2 tiles of a patch of ceil(m/tile) = T tile
+    rows), every tile counted in full (edge tiles compute their padding)."""
     T = (numpy.asarray(sizes, dtype=numpy.int64) + tile - 1) // tile
     return 2.0 * G * float(tile * tile) * float((T * (T + 1) // 2).sum())
 
@@ -348,7 +348,7 @@ def mapper_build_record(a, ctx, dev, N, G, metric, r, gain, steps, warmup, rank,
     m = bin_off[1:] - bin_off[:-1]
     sum_m2 = float((m * m).sum())
     flops = 2.0 * G * sum_m2 / world                          # this rank's share (LPT balances m^2)
-    flops_exec = executed_tile_flops(m, G) / world
+    flops_exec = executed_tile_flops(m, G, ctx.gemm_tile_fp64()) / world
     # the build has one host synchronisation (patch sizes come back to plan the batches): on a busy
     # host single builds are delayed by tens of ms, so the figure is the MEDIAN build; every build is listed
     ms = float(numpy.median(times))
@@ -371,7 +371,7 @@ def mapper_build_record(a, ctx, dev, N, G, metric, r, gain, steps, warmup, rank,
                         'traffic': None, 'kernel': 'gemm_kernel (FP64 DMMA)', 'kernel_ms': gms, 'flops': flops,
                         'flops_executed': flops_exec,
                         'conventions': '`frac`: SURVEY.md 8d\'s algorithmic 2*G*sum m_b^2, no symmetry credit (can exceed 1); '
-                                       '`frac_executed`: the 128x128 tiles the kernel runs (upper triangle of every '
+                                       '`frac_executed`: the output tiles (sctda_gemm_tile_fp64 squared) the kernel runs (upper triangle of every '
                                        'patch Gram tile, mirrored on the way out) -- the fraction of the tensor pipe '
                                        'actually used',
                         'peak_source': 'torch.matmul float64 6144^3 (cuBLAS DGEMM) probe in this run'}}

@@ -98,6 +98,11 @@ int32_t sctda_last_kernel_ms(sctda_ctx* ctx, float* out_ms);
  * Synchronises the host. */
 int32_t sctda_probe_l2_read_gbs(sctda_ctx* ctx, double* out_gbs);
 
+/* Side of the square output tiles of the FP64 contraction kernel (symmetric problems run the upper triangle of
+ * tiles and mirror it): what a caller needs to count the flops the kernel executes, next to the algorithmic
+ * 2*G*m^2 of SURVEY.md 8d (bench.py: roofline.frac_executed). */
+int32_t sctda_gemm_tile_fp64(void);
+
 /* ---- hot path (b): connectivity permutation test ------------------------------------------- */
 
 /*

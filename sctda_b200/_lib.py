@@ -72,6 +72,7 @@ SIGNATURES = {
     'sctda_root_scores': (c_i32, [c_ptr, c_i32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     'sctda_selftest_div': (c_i32, [c_ptr, c_i64, ctypes.POINTER(c_i64)]),
     'sctda_probe_l2_read_gbs': (c_i32, [c_ptr, ctypes.POINTER(c_f64)]),
+    'sctda_gemm_tile_fp64': (c_i32, []),
     'sctda_selftest_log1p': (c_i32, [c_ptr, c_i64, ctypes.POINTER(c_i64)]),
     'sctda_node_stats': (c_i32, [c_ptr, ctypes.POINTER(Graph), c_i32, c_ptr, c_i64, c_i32, c_ptr,
                                  c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
@@ -189,6 +190,9 @@ class Context(object):
         v = c_f64()
         self.check(self.lib.sctda_probe_l2_read_gbs(self.handle, ctypes.byref(v)))
         return float(v.value)
+
+    def gemm_tile_fp64(self):
+        return int(self.lib.sctda_gemm_tile_fp64())
 
     def workspace_bytes(self):
         return int(self.lib.sctda_workspace_bytes(self.handle))

@@ -27,6 +27,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "gemm.cuh"
 
 int sctda_internal_gram_bins(sctda_ctx* ctx, int G, const double* d_Xn, int64_t ldxn, int nprob,
                              const int32_t* d_prob_bin, const int32_t* d_bin_off, const int32_t* d_members,
@@ -1242,8 +1243,9 @@ extern "C" int32_t sctda_bin_cluster(sctda_ctx* ctx, int32_t G, const double* d_
             const int64_t m = h_off[order[end] + 1] - h_off[order[end]];
             if (end > pos && (bt.elems + (size_t)(m * m)) * 8 > budget) break;
             bt.elems += (size_t)(m * m);
-            const int64_t q = (m + 127) / 128;
-            bt.tiles.push_back(bt.tiles.back() + q * (q + 1) / 2);            // upper-triangular 128x128 tiles
+            const int64_t tile = sctda_gemm_tile(ctx->precision);
+            const int64_t q = (m + tile - 1) / tile;
+            bt.tiles.push_back(bt.tiles.back() + q * (q + 1) / 2);            // upper-triangular tiles of the contraction kernel
             bt.goff.push_back((int64_t)bt.elems);
             bt.chunks.push_back(bt.chunks.back() + (m + kColChunk - 1) / kColChunk);     // column chunks of the T kernel
             if (m * (max_K - 1) <= a.lev_cap && m > bt.max_lev) bt.max_lev = (int)m;

@@ -26,8 +26,20 @@
 
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 16, LDS = 20, STAGES = 3;
-constexpr int GEMM_THREADS = 256;
+#ifndef SCTDA_GEMM_STAGES
+#define SCTDA_GEMM_STAGES 3
+#endif
+// CTA tile BM x BN = kGemmTileFp64 squared (gemm.cuh): 128 -> 8 warps (4 x 2, warp tile 32 x 64), one CTA per SM;
+// 64 -> 4 warps (2 x 2, warp tile 32 x 32), three CTAs per SM.
+constexpr int BM = kGemmTileFp64, BN = kGemmTileFp64, BK = 16, LDS = 20, STAGES = SCTDA_GEMM_STAGES;
+constexpr int WARPS_M = BM / 32, WN = BN / 2, NJ = WN / 8;   // warps along M; columns and 8-column blocks of a warp tile
+constexpr int GEMM_THREADS = WARPS_M * 2 * 32;
+#ifndef SCTDA_GEMM_CTAS
+#define SCTDA_GEMM_CTAS 3
+#endif
+constexpr int GEMM_CTAS_PER_SM = BM == 128 ? 1 : SCTDA_GEMM_CTAS;
+static_assert(BM == 128 || BM == 64, "kGemmTileFp64 must be 128 or 64");
+static_assert(GEMM_THREADS == 2 * BM, "the staging assignments assume two threads per tile row");
 constexpr int STAGE_DOUBLES = (BM + BN) * LDS;
 constexpr size_t GEMM_SMEM = (size_t)STAGES * STAGE_DOUBLES * sizeof(double);
 
@@ -80,7 +92,7 @@ template <bool BULK>
 __device__ __forceinline__ void gemm_tile(const GemmArgs& a, const GemmProblem& pr, int ti, int tj, double* smem,
                                           bool mirror, uint64_t* bars, unsigned& it) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wm = warp & 3, wn = warp >> 2;                 // 4 x 2 warps, warp tile 32 x 64
+    const int wm = warp % WARPS_M, wn = warp / WARPS_M;      // WARPS_M x 2 warps, warp tile 32 x WN
     const int m0 = ti * BM, n0 = tj * BN;
     // this thread's cp.async assignments: chunk c = tid + 256*i  ->  row c/8, 16-byte column c%8
     const double* srcA[4];
@@ -101,10 +113,10 @@ __device__ __forceinline__ void gemm_tile(const GemmArgs& a, const GemmProblem& 
     // bulk path: thread t copies row (t & 127) of A (t < 128) or of B: one 128-byte TMA bulk copy per
     // thread and stage (the copy instruction is warp-uniform in hardware, so 32 lanes are 32 issues)
     const double* bulk_row = nullptr;
-    const int bulk_dst = ((tid >> 7) ? BM * LDS : 0) + (tid & 127) * LDS;
+    const int bulk_dst = ((tid >= BM) ? BM * LDS : 0) + (tid % BM) * LDS;
     if (BULK) {
-        const int r = tid & 127;
-        if (tid < 128) {
+        const int r = tid % BM;
+        if (tid < BM) {
             const int ra = min(m0 + r, pr.na - 1);
             bulk_row = a.X + (pr.rows_a ? (int64_t)pr.rows_a[ra] : (int64_t)(pr.row0_a + ra)) * a.ldx;
         } else {
@@ -128,11 +140,11 @@ __device__ __forceinline__ void gemm_tile(const GemmArgs& a, const GemmProblem& 
             cp_async_16_zfill(sB + dst_off[i], bytes ? (const void*)(srcB[i] + k0) : (const void*)a.X, bytes);
         }
     };
-    double acc[4][8][2];
+    double acc[4][NJ][2];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        for (int j = 0; j < NJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
     if (BULK) {
         if (tid == 0)
@@ -163,18 +175,18 @@ __device__ __forceinline__ void gemm_tile(const GemmArgs& a, const GemmProblem& 
             cp_async_commit();
         }
         const double* sA = smem + (size_t)slot * STAGE_DOUBLES + (wm * 32 + fr) * LDS + fc;
-        const double* sB = smem + (size_t)slot * STAGE_DOUBLES + BM * LDS + (wn * 64 + fr) * LDS + fc;
+        const double* sB = smem + (size_t)slot * STAGE_DOUBLES + BM * LDS + (wn * WN + fr) * LDS + fc;
 #pragma unroll
         for (int kk = 0; kk < BK / 4; ++kk) {
-            double fa[4], fb[8];
+            double fa[4], fb[NJ];
 #pragma unroll
             for (int i = 0; i < 4; ++i) fa[i] = sA[i * 8 * LDS + kk * 4];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) fb[j] = sB[j * 8 * LDS + kk * 4];
+            for (int j = 0; j < NJ; ++j) fb[j] = sB[j * 8 * LDS + kk * 4];
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < 8; ++j) dmma_884(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
+                for (int j = 0; j < NJ; ++j) dmma_884(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
         }
     }
     if (!BULK) cp_async_wait<0>();
@@ -188,10 +200,10 @@ __device__ __forceinline__ void gemm_tile(const GemmArgs& a, const GemmProblem& 
         const int64_t gr = pr.rows_a ? (int64_t)pr.rows_a[r] : (int64_t)(pr.row0_a + r);
         const double sqr = (a.epilogue == EPI_EUCLID) ? a.sq[gr] : 0.0;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < NJ; ++j) {
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-                const int c = n0 + wn * 64 + j * 8 + fc * 2 + e;
+                const int c = n0 + wn * WN + j * 8 + fc * 2 + e;
                 if (c >= pr.nb) continue;
                 double v = acc[i][j][e];
                 if (a.epilogue != EPI_GRAM) {
@@ -232,7 +244,7 @@ __device__ __forceinline__ void batched_tile(const GemmArgs& a, int64_t t, doubl
 }
 
 template <bool BULK>
-__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(GemmArgs a) {
+__global__ void __launch_bounds__(GEMM_THREADS, GEMM_CTAS_PER_SM) gemm_kernel(GemmArgs a) {
     extern __shared__ __align__(16) double smem[];
     __shared__ __align__(8) uint64_t bars[STAGES];
     unsigned it = 0;
@@ -326,8 +338,9 @@ int launch_gemm(sctda_ctx* ctx, const GemmArgs& a, int64_t tiles_hint, cudaStrea
         SCTDA_CUDA(ctx, cudaFuncSetAttribute(gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
         ctx->attr_done |= 2u;
     }
-    int64_t grid = tiles_hint > 0 ? tiles_hint : ctx->sm_count;
-    if (grid > ctx->sm_count) grid = ctx->sm_count;          // persistent: one CTA per SM
+    const int64_t resident = (int64_t)ctx->sm_count * GEMM_CTAS_PER_SM;
+    int64_t grid = tiles_hint > 0 ? tiles_hint : resident;
+    if (grid > resident) grid = resident;                    // persistent: every resident CTA slot
     if (a.grid_ctas > 0) grid = a.grid_ctas;
     if (grid < 1) grid = 1;
     if (a.untimed) {
@@ -365,6 +378,8 @@ int sctda_internal_gram_bins(sctda_ctx* ctx, int G, const double* d_Xn, int64_t 
     a.grid_ctas = grid_ctas; a.untimed = untimed ? 1 : 0; a.tiles_per_cta = tiles_per_cta;
     return launch_gemm(ctx, a, 0, st, ldxn >= ((int64_t)G + 15) / 16 * 16, reuse_split);
 }
+
+extern "C" int32_t sctda_gemm_tile_fp64(void) { return kGemmTileFp64; }
 
 extern "C" int32_t sctda_row_normalize_f64(sctda_ctx* ctx, int32_t N, int32_t G, const double* d_X, int64_t ldx,
                                            int32_t mode, double* d_Xn, int64_t ldxn, double* d_sq, void* stream) {

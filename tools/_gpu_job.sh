@@ -1,8 +1,5 @@
-set -x
-python -m pytest tests -m gpu -x -q 2>&1 | tail -5
-python bench.py --steps 3 --warmup 3 > gpurun_out/bench_final1.json 2> gpurun_out/bench_final1.err; tail -c 300 gpurun_out/bench_final1.json
-python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; tail -c 1500 gpurun_out/bench_ref.json
-B="python bench.py --steps 1 --warmup 1 --perms 500 --no-cpu --no-rooted"
-ncu --metrics gpu__time_duration.sum --clock-control none -k "$(cat tools/own_kernels.regex)" --csv --log-file gpurun_out/launches_r02.csv $B > gpurun_out/ncu2.log 2>&1
-tail -2 gpurun_out/ncu2.log | cut -c1-300
-python __graft_entry__.py --smoke 2>&1 | tail -3
+M="python tools/mapper_run.py 100000 2000 30 3 euclidean 2"
+cp sctda_b200/csrc/libsctda_b200.so /tmp/cur.so
+$M | tail -1 | cut -c1-60
+for v in c4s2 c3s2 c2s4; do cp build/base/lib$v.so sctda_b200/csrc/libsctda_b200.so; echo $v; $M | tail -1 | cut -c1-60; done
+cp /tmp/cur.so sctda_b200/csrc/libsctda_b200.so
