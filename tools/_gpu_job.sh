@@ -1,5 +1,2 @@
-M="python tools/mapper_run.py 100000 2000 30 3 euclidean 2"
-cp sctda_b200/csrc/libsctda_b200.so /tmp/cur.so
-$M | tail -1 | cut -c1-60
-for v in c4s2 c3s2 c2s4; do cp build/base/lib$v.so sctda_b200/csrc/libsctda_b200.so; echo $v; $M | tail -1 | cut -c1-60; done
-cp /tmp/cur.so sctda_b200/csrc/libsctda_b200.so
+set -x
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29551 bench.py --gpus 8 --steps 3 --warmup 3 > gpurun_out/bench_n8d.json 2> gpurun_out/bench_n8d.err; tail -c 300 gpurun_out/bench_n8d.json; tail -3 gpurun_out/bench_n8d.err
