@@ -438,3 +438,47 @@ def test_large_components_use_the_other_staging_paths(n_cells):
     assert torch.equal(exa, exb) and torch.equal(tia, tib)
     numpy.testing.assert_allclose(sca.cpu().numpy(), scb.cpu().numpy(), rtol=1e-13, atol=0, equal_nan=True)
     assert torch.isfinite(sca).any()
+
+
+def _sharded_pvalues_worker(rank, ws, port, prefix, out_dir):
+    import torch.distributed as dist
+    from sctda_b200 import graph
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=ws)
+    try:
+        c = graph.UnrootedGraph(prefix, prefix + '.all.tsv', groups=False)
+        genes = sorted(c.gene_row.keys())
+        perms = graph.reference_perm_indices(32, int(c.samples.size), numpy.random.RandomState(3))
+        pv, ties = c.connectivity_pvalues(genes, n=32, perms=perms, return_ties=True)
+        numpy.save(os.path.join(out_dir, 'pv%d.npy' % rank), numpy.asarray(pv))
+        numpy.save(os.path.join(out_dir, 'ti%d.npy' % rank), numpy.asarray(ties))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gene_sharded_pvalues_under_a_process_group_equal_the_single_process_result(tmp_path):
+    """UnrootedGraph.connectivity_pvalues(perms=...) under torch.distributed (two ranks sharing cuda:0, gloo): the tile
+    plan is broadcast, every rank takes every second 128-gene tile of the planned order, the counts are gathered and
+    put back at their gene positions -- p-values and tie counts of every gene equal the single-process call."""
+    _gpu()
+    import socket
+    import torch.multiprocessing as mp
+    from oracle import gen_golden
+    from sctda_b200 import graph
+    prefix = str(tmp_path / 'case')
+    gen_golden.write_case(prefix, n_cells=300, n_genes=420, n_nodes=50, seed=5)       # 421 columns: four tiles
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_sharded_pvalues_worker, args=(2, port, prefix, str(tmp_path)), nprocs=2, join=True)
+    c = graph.UnrootedGraph(prefix, prefix + '.all.tsv', groups=False)
+    genes = sorted(c.gene_row.keys())
+    perms = graph.reference_perm_indices(32, int(c.samples.size), numpy.random.RandomState(3))
+    pv, ties = c.connectivity_pvalues(genes, n=32, perms=perms, return_ties=True)
+    assert len(genes) > 3 * 128
+    for r in range(2):
+        numpy.testing.assert_array_equal(numpy.load(str(tmp_path / ('pv%d.npy' % r))), numpy.asarray(pv))
+        numpy.testing.assert_array_equal(numpy.load(str(tmp_path / ('ti%d.npy' % r))), numpy.asarray(ties))
+    assert 0.0 < float(numpy.mean(pv)) < 1.0
