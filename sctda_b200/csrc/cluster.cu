@@ -1255,11 +1255,15 @@ extern "C" int32_t sctda_bin_cluster(sctda_ctx* ctx, int32_t G, const double* d_
         batches.push_back(std::move(bt));
         pos = end;
     }
-    // Two-stream pipeline (contraction of batch i+1 over the MST / selection of batch i): measured on
-    // B200 it gains 1 % on a 4-batch build and makes single-batch builds jitter by up to +30 % (the
-    // cross-stream hand-over), so it is opt-in (SCTDA_PIPELINE=1, at least two batches) and the
-    // default runs every kernel on the caller's stream.
-    const bool pipe = linkage == 0 && batches.size() >= 2 && getenv("SCTDA_PIPELINE") && atoi(getenv("SCTDA_PIPELINE")) != 0;
+    // Two-stream pipeline (contraction of batch i+1 over the MST / selection of batch i).  Measured on a B200 with the
+    // three-CTA-per-SM contraction: the 7-batch 100k x 2k build on one GPU goes from 1,000 to 970 ms (the contraction
+    // slows from 824 to 861 ms next to the MST kernels, the MST chains disappear behind it); with one or two batches
+    // the cross-stream hand-over only adds jitter (up to +30 % on single-batch builds), so the pipeline runs from
+    // three batches on (SCTDA_PIPELINE=0 / 1 forces it off / on from two batches) and the default otherwise runs
+    // every kernel on the caller's stream.
+    const char* pipe_env = getenv("SCTDA_PIPELINE");
+    const size_t pipe_min = pipe_env ? (atoi(pipe_env) != 0 ? 2 : (size_t)-1) : 3;
+    const bool pipe = linkage == 0 && batches.size() >= pipe_min;
     cudaStream_t aux_st = pipe ? ctx->aux_stream : st;
     // allocate both buffers up front (no reallocation while the pipeline runs)
     size_t need0 = 0, need1 = 0, meta0 = 0, meta1 = 0;
