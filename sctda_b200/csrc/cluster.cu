@@ -1178,6 +1178,11 @@ extern "C" int32_t sctda_bin_cluster(sctda_ctx* ctx, int32_t G, const double* d_
     }
     const int linkage = ctx->linkage;             // 0 single (MST), 1 average, 2 ward, 3 complete (sctda_set_linkage)
     if (linkage != 0) budget /= 2;                // the chain works on a copy of every patch's distance matrix
+    // (Cutting a build that fits one buffer into three batches so that the pipeline below can hide the MST chains of
+    // its large patches was measured on a rank's share of the 8-GPU 100k x 2k build: 134 -> 158 ms.  Every batch of
+    // such a shard still holds patches of 8,000+ cells, so a 20 ms chain stays exposed at the end and the contraction
+    // pays for the ones it hides.)
+    const char* pipe_env = getenv("SCTDA_PIPELINE");
     const size_t aux_bytes = M * (8 * (2 * kMaxK + 4) + 4 * 4 + (kMaxK - 1)) + 256;
     unsigned char* aux = (unsigned char*)sctda_ws(ctx, WS_CLUSTER3, aux_bytes);
     if (!aux) return SCTDA_ERR_NOMEM;
@@ -1261,7 +1266,6 @@ extern "C" int32_t sctda_bin_cluster(sctda_ctx* ctx, int32_t G, const double* d_
     // the cross-stream hand-over only adds jitter (up to +30 % on single-batch builds), so the pipeline runs from
     // three batches on (SCTDA_PIPELINE=0 / 1 forces it off / on from two batches) and the default otherwise runs
     // every kernel on the caller's stream.
-    const char* pipe_env = getenv("SCTDA_PIPELINE");
     const size_t pipe_min = pipe_env ? (atoi(pipe_env) != 0 ? 2 : (size_t)-1) : 3;
     const bool pipe = linkage == 0 && batches.size() >= pipe_min;
     cudaStream_t aux_st = pipe ? ctx->aux_stream : st;
