@@ -27,15 +27,18 @@
 namespace {
 
 #ifndef SCTDA_GEMM_STAGES
-#define SCTDA_GEMM_STAGES 3
+#define SCTDA_GEMM_STAGES (SCTDA_GEMM_TILE == 64 ? 4 : 3)
 #endif
 // CTA tile BM x BN = kGemmTileFp64 squared (gemm.cuh): 128 -> 8 warps (4 x 2, warp tile 32 x 64), one CTA per SM;
-// 64 -> 4 warps (2 x 2, warp tile 32 x 32), three CTAs per SM.
+// 64 -> 4 warps (2 x 2, warp tile 32 x 32), TWO CTAs per SM with a four-stage ring (164 KB of shared memory, 90 KB
+// left to L1, which the .ca copies use).  Measured on the 100k x 2k patch tiles (B200, gemm_ms of tools/mapper_run.py):
+// 128-tile / 1 CTA / 3 stages 809 ms; 64-tile: 3 CTAs x 3 stages 785, 2 x 3 775, 2 x 4 767, 2 x 5 782, 4 x 2 832,
+// 1 x 8 1,024 (and 888 / 826 for the first two with .cg copies).
 constexpr int BM = kGemmTileFp64, BN = kGemmTileFp64, BK = 16, LDS = 20, STAGES = SCTDA_GEMM_STAGES;
 constexpr int WARPS_M = BM / 32, WN = BN / 2, NJ = WN / 8;   // warps along M; columns and 8-column blocks of a warp tile
 constexpr int GEMM_THREADS = WARPS_M * 2 * 32;
 #ifndef SCTDA_GEMM_CTAS
-#define SCTDA_GEMM_CTAS 3
+#define SCTDA_GEMM_CTAS 2
 #endif
 constexpr int GEMM_CTAS_PER_SM = BM == 128 ? 1 : SCTDA_GEMM_CTAS;
 static_assert(BM == 128 || BM == 64, "kGemmTileFp64 must be 128 or 64");
@@ -45,7 +48,14 @@ constexpr size_t GEMM_SMEM = (size_t)STAGES * STAGE_DOUBLES * sizeof(double);
 
 __device__ __forceinline__ void cp_async_16_zfill(void* smem_dst, const void* gmem_src, int src_bytes) {
     unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    // .ca: through L1.  With .cg every 16-byte copy is its own L2 request and comes back as a whole 32-byte sector:
+    // twice the operand bytes on the L2 -> SM fabric (ncu: 553 GB against 276 GB of operands per launch), which the
+    // three-CTA 64-tile kernel felt: 826 -> 785 ms on the 100k x 2k patch tiles.
+#ifdef SCTDA_GEMM_CPASYNC_CG
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gmem_src), "r"(src_bytes) : "memory");
+#else
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gmem_src), "r"(src_bytes) : "memory");
+#endif
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>

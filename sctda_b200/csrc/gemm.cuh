@@ -5,7 +5,7 @@
 
 enum { EPI_GRAM = 0, EPI_EUCLID = 1, EPI_CORR = 2 };
 
-// Side of the square output tile of the FP64 kernel (dist.cu): 64 (4 warps, three CTAs per SM; measured 7-13 % faster
+// Side of the square output tile of the FP64 kernel (dist.cu): 64 (4 warps, two CTAs per SM; measured 5-13 % faster
 // than one 8-warp CTA on 128 x 128 tiles: independent CTAs fill each other's per-stage barriers and tile
 // prologues / epilogues); the opt-in tcgen05 kernel always works on 128 x 128.
 // tile_prefix of a batched launch counts the upper-triangular tiles of THIS size (sctda_gemm_tile(precision)).
