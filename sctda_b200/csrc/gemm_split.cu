@@ -86,6 +86,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
     }
 }
 __device__ __forceinline__ void cp_async_16(uint32_t smem_dst, const void* gmem_src) {
+    // .cg (L2 only).  Through L1 (.ca), which pays in the FP64 kernel (dist.cu), this kernel is slower: 10.4 -> 12.9 ms
+    // on the config-2 patch tiles; its 192 KB of stages leave L1 too small to merge the two halves of a sector.
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gmem_src) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
