@@ -401,6 +401,13 @@ __global__ void __launch_bounds__(NW * 32, 1) conn_perm_wide_kernel(WideArgs a) 
                 k = kn; beg = begn; end = endn;
             }
             __syncthreads();
+#ifndef SCTDA_CONNW_NO_PM_PREFETCH
+            // The node values of this permutation (1 MB, written over the whole node phase) have mostly left L2 by now
+            // (148 CTAs x 1 MB next to the tile): ask for all of them at once, so that the rows below are served from
+            // L2 instead of paying a DRAM round trip each, one dependent row after the other.
+            for (int i = threadIdx.x; i < a.V * (kT / 32); i += NW * 32)
+                asm volatile("prefetch.global.L2 [%0];" :: "l"(pm + (size_t)i * 32));
+#endif
             // ---- tot (ref:984, this warp's nodes in ascending order) and p'Ap on the un-normalised values; the
             // 1/tot^2 is applied once (ref:988-989) ----
             double part[kGPL], tot[kGPL];
