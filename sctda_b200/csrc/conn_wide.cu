@@ -31,7 +31,8 @@
 // value cost more than the 4 wavefronts of the lookup); two or three independent warp groups per CTA (named
 // barriers) working on different permutation chunks so that one group's adjacency phase (20 % of the time, LSU
 // pipe nearly idle) overlaps the others' gathers (+5 % / +35 % time: the phases share one L1/L2 path and the
-// smaller groups have fewer rows in flight); rows stored COMPACTED to their non-empty sectors
+// smaller groups have fewer rows in flight); `prefetch.global.L1` of the node values the NEXT adjacency row reads
+// (+10 % time); rows stored COMPACTED to their non-empty sectors
 // (a lane's sector at popc(mask & lanes below)), so that the fetched sectors are contiguous.  The LSU data pipe
 // charges one wavefront per quad of lanes with an active lane, not per 128-byte line: wavefronts per
 // gene*permutation did not move (3,900 -> 3,900) and the extra offset lookups made the kernel 40 % slower.
