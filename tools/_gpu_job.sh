@@ -1,1 +1,3 @@
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29571 bench.py --gpus 8 --steps 3 --warmup 3 > gpurun_out/bench_n8e.json 2> gpurun_out/bench_n8e.err; tail -c 200 gpurun_out/bench_n8e.json
+M="python tools/mapper_run.py 100000 2000 30 3 euclidean 1"
+SCTDA_PIPELINE=0 ncu --set full --clock-control none --import-source on -k regex:gemm_kernel -s 2 -c 1 -o gpurun_out/prof_gemm_r02 -f $M > gpurun_out/ncu4.log 2>&1
+tail -2 gpurun_out/ncu4.log | cut -c1-200
