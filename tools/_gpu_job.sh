@@ -1,3 +1,1 @@
-M="python tools/mapper_run.py 100000 2000 30 3 euclidean 1"
-SCTDA_PIPELINE=0 ncu --set full --clock-control none --import-source on -k regex:gemm_kernel -s 2 -c 1 -o gpurun_out/prof_gemm_r02 -f $M > gpurun_out/ncu4.log 2>&1
-tail -2 gpurun_out/ncu4.log | cut -c1-200
+for o in none density pca; do python tools/conn_probe.py --genes 8192 --perms 1184 --order $o --reps 2 | grep -o '"order": "[a-z]*"\|"kernel_ms": [^]]*]\|frac_of_8.2e7": [0-9.]*' | paste - - -; done
