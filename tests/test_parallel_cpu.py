@@ -174,3 +174,24 @@ def test_tile_shard_positions_partition_the_planned_order():
                 assert (numpy.diff(p) > 0).all()
             sizes = [p.size for p in parts]
             assert max(sizes) - min(sizes) <= 128
+
+
+def test_patch_dealer_charges_the_chain_of_the_largest_patch():
+    """assign_patches_lpt: every patch goes to exactly one rank; with the chain term the rank that holds the largest
+    patch (the longest MST chain) carries fewer Gram-tile entries than the others, without it the m^2 loads are level."""
+    from sctda_b200 import parallel
+    rs = numpy.random.RandomState(7)
+    sizes = numpy.concatenate([[15432, 13027, 12502, 11669, 11490, 11317, 11187, 10546], rs.randint(4200, 10000, 48),
+                               rs.randint(50, 4000, 800), [0, 0, 1]])
+    for chain in (False, True):
+        parts = parallel.assign_patches_lpt(sizes, 8, chain=chain)
+        allp = numpy.sort(numpy.concatenate(parts))
+        assert allp.tolist() == list(range(sizes.size))
+        load = numpy.array([float((sizes[p].astype(numpy.float64) ** 2).sum()) for p in parts])
+        top = int(numpy.argmax([sizes[p].max() for p in parts]))
+        if chain:
+            assert load[top] < numpy.delete(load, top).min()
+            assert load.max() / load.min() < 1.25
+        else:
+            assert load.max() / load.min() < 1.02
+    assert [p.tolist() for p in parallel.assign_patches_lpt(sizes, 8)] == [p.tolist() for p in parallel.assign_patches_lpt(sizes, 8)]
