@@ -205,7 +205,8 @@ int32_t sctda_conn_perm_test(sctda_ctx* ctx, const sctda_graph* graph,
  * order d_gene_order [G] (a permutation of 0..G-1; NULL = table order).  Results are written at the
  * ORIGINAL gene positions, so the order never changes what is computed, only which genes share
  * a 32-byte sector of the transposed table: the kernel never requests sectors that hold only
- * zeros, and genes with similar supports empty more sectors (sctda_gene_order proposes an order).
+ * zeros, and genes with similar supports empty more sectors and whole rows (the host layer's
+ * sctda_b200/geneorder.py proposes an order).
  * sctda_conn_perm_test with perm_gene_stride == 0 is this call with d_gene_order == NULL.
  * Needs S <= 65,535 (16-bit staged permutation rows); larger graphs and per-gene permutation
  * blocks run on the 32-gene kernel behind sctda_conn_perm_test.
